@@ -1,0 +1,244 @@
+// extern "C" entry points of libbatman_b200.so (declared in include/batman_b200.h).
+#include <stdarg.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "model.h"
+
+namespace bk {
+
+thread_local char g_err[512] = "";
+
+int set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    return set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+}
+
+struct ProfEvent { cudaEvent_t a, b; int cat; };
+static bool g_prof_on = false;
+static std::vector<ProfEvent> g_prof_events;
+
+ProfScope::ProfScope(int cat, cudaStream_t s) : st(s), idx(-1) {
+    if (!g_prof_on) return;
+    ProfEvent e; e.cat = cat;
+    if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+    cudaEventRecord(e.a, st);
+    g_prof_events.push_back(e);
+    idx = (int)g_prof_events.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof_events[idx].b, st);
+}
+
+// kernels (other translation units)
+int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar, cudaStream_t st);
+int launch_var(const bk_gp_s* h, int q, const double* kstar, long k, double* std_out, cudaStream_t st);
+int launch_pack_w(const double* w, int n, double* out, cudaStream_t st);
+int launch_sobol(const bk_gp_s* h, int q, const double* a, const double* b, uint64_t seed, const int* mkind,
+                 const double* mpar, long row_lo, long count, int second, double shift, double* partials,
+                 cudaStream_t st);
+int launch_design_rows(uint64_t seed, long row_lo, long count, int p, const int* mkind, const double* mpar,
+                       int stream_id, double* out, cudaStream_t st);
+int launch_sobol_y(const double* y, long ld_block, long count, int p, int F, int second, const double* shift,
+                   double* partials, cudaStream_t st);
+int launch_reduce_slots(const double* partials, int F, int nsums, double* totals, cudaStream_t st);
+int launch_finalize(const double* totals, long N, int p, int F, int second, double* out, cudaStream_t st);
+size_t sobol_result_len(int p, int F);
+int sobol_nsums_host(int p, int second);
+int sobol_nslots_host();
+
+constexpr long PRED_CHUNK_ALIGN = 256;   // k_predict covers 2 tiles of 128 points per CTA
+
+}  // namespace bk
+
+using namespace bk;
+
+extern "C" {
+
+int bk_version(void) { return 100; }
+const char* bk_last_error(void) { return g_err; }
+
+int bk_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    BK_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    BK_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return 0;
+}
+
+int bk_profile_enable(int on) {
+    g_prof_on = on != 0;
+    return 0;
+}
+
+int bk_profile_read(double* ms_by_cat, long* launches_by_cat) {
+    if (!ms_by_cat || !launches_by_cat) return set_error("bk_profile_read: NULL pointer");
+    for (int c = 0; c < PROF_NCAT; ++c) { ms_by_cat[c] = 0.0; launches_by_cat[c] = 0; }
+    for (auto& e : g_prof_events) {
+        BK_CUDA(cudaEventSynchronize(e.b));
+        float ms = 0.f;
+        BK_CUDA(cudaEventElapsedTime(&ms, e.a, e.b));
+        ms_by_cat[e.cat] += ms;
+        launches_by_cat[e.cat] += 1;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    g_prof_events.clear();
+    return 0;
+}
+
+int bk_gp_padded_dim(int p) { return padded_dim(p); }
+int bk_gp_padded_n(int n) { return padded_n(n); }
+size_t bk_gp_wtiles_len(int n) { return (size_t)padded_n(n) * padded_n(n); }
+
+int bk_gp_create(bk_gp_t* out, int n, int p, int m) {
+    if (!out) return set_error("bk_gp_create: out is NULL");
+    if (n < 1 || p < 1 || m < 1) return set_error("bk_gp_create: n, p, m must be >= 1 (got %d, %d, %d)", n, p, m);
+    const int P = padded_dim(p);
+    if (P < 0) return set_error("bk_gp_create: input dimension %d > %d is not instantiated", p, MAX_P);
+    bk_gp_s* h = new (std::nothrow) bk_gp_s();
+    if (!h) return set_error("bk_gp_create: out of host memory");
+    h->n = n; h->p = p; h->P = P; h->m = m; h->n_pad = padded_n(n);
+    for (int c = 0; c < MAX_P; ++c) { h->scale[c] = 1.0; h->mn[c] = 0.0; }
+    h->out.resize(m);
+    *out = h;
+    return 0;
+}
+
+int bk_gp_destroy(bk_gp_t h) {
+    delete h;
+    return 0;
+}
+
+int bk_gp_set_output(bk_gp_t h, int q, int kind, double c0, double c1, double kdiag, const double* ls_host,
+                     const double* xs_dev, const double* alpha_dev, const double* w_tiles_dev, double y_mean,
+                     double y_std) {
+    if (!h) return set_error("bk_gp_set_output: NULL handle");
+    if (q < 0 || q >= h->m) return set_error("bk_gp_set_output: output %d out of range [0, %d)", q, h->m);
+    if (kind < BK_MATERN12 || kind > BK_MATERN_INF) return set_error("bk_gp_set_output: unknown kernel kind %d", kind);
+    if (!ls_host || !xs_dev || !alpha_dev) return set_error("bk_gp_set_output: NULL pointer");
+    GpOutput& o = h->out[q];
+    o.kind = kind; o.c0 = c0; o.c1 = c1; o.kdiag = kdiag; o.y_mean = y_mean; o.y_std = y_std;
+    for (int c = 0; c < MAX_P; ++c) o.ls[c] = c < h->p ? ls_host[c] : 1.0;
+    o.xs = xs_dev; o.alpha = alpha_dev; o.wt = w_tiles_dev;
+    return 0;
+}
+
+int bk_gp_set_scaler(bk_gp_t h, const double* scale_host, const double* min_host) {
+    if (!h) return set_error("bk_gp_set_scaler: NULL handle");
+    for (int c = 0; c < h->p; ++c) {
+        h->scale[c] = scale_host ? scale_host[c] : 1.0;
+        h->mn[c] = min_host ? min_host[c] : 0.0;
+    }
+    return 0;
+}
+
+int bk_pack_w(const double* w_dev, int n, double* w_tiles_dev, void* stream) {
+    if (!w_dev || !w_tiles_dev) return set_error("bk_pack_w: NULL pointer");
+    return launch_pack_w(w_dev, n, w_tiles_dev, (cudaStream_t)stream);
+}
+
+size_t bk_gp_predict_workspace(bk_gp_t h, long k, int want_std) {
+    if (!h || !want_std || k <= 0) return 0;
+    long kk = (k + PRED_CHUNK_ALIGN - 1) / PRED_CHUNK_ALIGN * PRED_CHUNK_ALIGN;
+    const long cap = 148L * TILE_T * 4;   // 4 test tiles per SM per chunk keeps K* (n_pad * 8 B per point) L2-friendly
+    if (kk > cap) kk = cap;
+    return (size_t)kk * h->n_pad * sizeof(double);
+}
+
+int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, double* std_dev, void* workspace_dev,
+                  size_t workspace_bytes, void* stream) {
+    if (!h) return set_error("bk_gp_predict: NULL handle");
+    if (k < 0) return set_error("bk_gp_predict: negative point count");
+    if (k == 0) return 0;
+    if (!pts_dev || !mean_dev) return set_error("bk_gp_predict: NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!std_dev) {
+        for (int q = 0; q < h->m; ++q)
+            if (int rc = launch_predict(h, q, pts_dev, k, mean_dev, nullptr, st)) return rc;
+        return 0;
+    }
+    const size_t per_point = (size_t)h->n_pad * sizeof(double);
+    long chunk = (long)(workspace_bytes / per_point) / PRED_CHUNK_ALIGN * PRED_CHUNK_ALIGN;
+    if (!workspace_dev || chunk < PRED_CHUNK_ALIGN)
+        return set_error("bk_gp_predict: sigma needs a workspace of at least %zu bytes (got %zu)",
+                         per_point * PRED_CHUNK_ALIGN, workspace_bytes);
+    double* kstar = (double*)workspace_dev;
+    for (long lo = 0; lo < k; lo += chunk) {
+        const long cnt = (k - lo) < chunk ? (k - lo) : chunk;
+        for (int q = 0; q < h->m; ++q) {
+            if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, kstar, st)) return rc;
+            if (int rc = launch_var(h, q, kstar, cnt, std_dev + lo * h->m, st)) return rc;
+        }
+    }
+    return 0;
+}
+
+int bk_sobol_nsums(int p, int second_order) { return sobol_nsums_host(p, second_order); }
+int bk_sobol_nslots(void) { return sobol_nslots_host(); }
+
+int bk_design_rows(uint64_t seed, long row_lo, long count, int p, const int* marg_kind_host,
+                   const double* marg_par_host, int stream_id, double* out_dev, void* stream) {
+    if (!marg_kind_host || !marg_par_host || !out_dev) return set_error("bk_design_rows: NULL pointer");
+    for (int c = 0; c < p; ++c)
+        if (marg_kind_host[c] != BK_UNIFORM && marg_kind_host[c] != BK_NORMAL)
+            return set_error("bk_design_rows: marginal %d has unknown kind %d", c, marg_kind_host[c]);
+    return launch_design_rows(seed, row_lo, count, p, marg_kind_host, marg_par_host, stream_id, out_dev,
+                              (cudaStream_t)stream);
+}
+
+int bk_sobol_accumulate(bk_gp_t h, const double* a_dev, const double* b_dev, uint64_t seed, const int* marg_kind_host,
+                        const double* marg_par_host, long row_lo, long count, int second_order,
+                        const double* shift_host, double* partials_dev, void* stream) {
+    if (!h || !partials_dev) return set_error("bk_sobol_accumulate: NULL pointer");
+    if ((a_dev == nullptr) != (b_dev == nullptr)) return set_error("bk_sobol_accumulate: a_dev and b_dev must both be given or both NULL");
+    if (!a_dev && (!marg_kind_host || !marg_par_host))
+        return set_error("bk_sobol_accumulate: no base samples and no marginals to generate them from");
+    if (!a_dev)
+        for (int c = 0; c < h->p; ++c)
+            if (marg_kind_host[c] != BK_UNIFORM && marg_kind_host[c] != BK_NORMAL)
+                return set_error("bk_sobol_accumulate: marginal %d has unknown kind %d", c, marg_kind_host[c]);
+    if (count <= 0) return 0;
+    for (int q = 0; q < h->m; ++q)
+        if (int rc = launch_sobol(h, q, a_dev, b_dev, seed, marg_kind_host, marg_par_host, row_lo, count,
+                                  second_order ? 1 : 0, shift_host ? shift_host[q] : 0.0, partials_dev,
+                                  (cudaStream_t)stream))
+            return rc;
+    return 0;
+}
+
+int bk_sobol_accumulate_y(const double* y_dev, long ld_block, long count, int p, int F, int second_order,
+                          const double* shift_dev, double* partials_dev, void* stream) {
+    if (!y_dev || !shift_dev || !partials_dev) return set_error("bk_sobol_accumulate_y: NULL pointer");
+    if (p < 1 || F < 1) return set_error("bk_sobol_accumulate_y: p and F must be >= 1");
+    if (count <= 0) return 0;
+    return launch_sobol_y(y_dev, ld_block, count, p, F, second_order ? 1 : 0, shift_dev, partials_dev,
+                          (cudaStream_t)stream);
+}
+
+int bk_sobol_reduce_slots(const double* partials_dev, int F, int nsums, double* totals_dev, void* stream) {
+    if (!partials_dev || !totals_dev) return set_error("bk_sobol_reduce_slots: NULL pointer");
+    return launch_reduce_slots(partials_dev, F, nsums, totals_dev, (cudaStream_t)stream);
+}
+
+size_t bk_sobol_result_len(int p, int F) { return sobol_result_len(p, F); }
+
+int bk_sobol_finalize(const double* totals_dev, long N, int p, int F, int second_order, double* out_dev,
+                      void* stream) {
+    if (!totals_dev || !out_dev) return set_error("bk_sobol_finalize: NULL pointer");
+    if (N < 2) return set_error("bk_sobol_finalize: N must be >= 2");
+    return launch_finalize(totals_dev, N, p, F, second_order ? 1 : 0, out_dev, (cudaStream_t)stream);
+}
+
+}  // extern "C"

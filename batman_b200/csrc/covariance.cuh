@@ -1,0 +1,38 @@
+// Stationary covariance factors, rounded exactly like the numpy expressions of
+// sklearn:kernels.py:1716-1730 (Matern) and 1557-1563 (RBF): explicit _rn
+// intrinsics so that nvcc cannot contract a mul+add into an FMA where numpy
+// rounds twice.  The squared scaled distance `s` is accumulated by the caller
+// in scipy cdist order (sequential, non-fused s += d*d).
+#pragma once
+#include "../../include/batman_b200.h"
+
+namespace bk {
+
+constexpr double SQRT3 = 1.7320508075688772;   // math.sqrt(3)
+constexpr double SQRT5 = 2.23606797749979;     // math.sqrt(5)
+
+template <int KIND>
+__device__ __forceinline__ double stationary(double s) {
+    if constexpr (KIND == BK_MATERN12) {
+        return exp(-sqrt(s));                                       // np.exp(-dists)
+    } else if constexpr (KIND == BK_MATERN32) {
+        double t = __dmul_rn(sqrt(s), SQRT3);                       // K = dists * math.sqrt(3)
+        return __dmul_rn(__dadd_rn(1.0, t), exp(-t));               // (1.0 + K) * np.exp(-K)
+    } else if constexpr (KIND == BK_MATERN52) {
+        double t = __dmul_rn(sqrt(s), SQRT5);                       // K = dists * math.sqrt(5)
+        double q = __ddiv_rn(__dmul_rn(t, t), 3.0);                 // K**2 / 3.0
+        return __dmul_rn(__dadd_rn(__dadd_rn(1.0, t), q), exp(-t)); // (1.0 + K + K**2/3.0) * np.exp(-K)
+    } else if constexpr (KIND == BK_RBF) {
+        return exp(__dmul_rn(-0.5, s));                             // np.exp(-0.5 * sqeuclidean)
+    } else {
+        double d = sqrt(s);
+        return exp(-__dmul_rn(__dmul_rn(d, d), 0.5));               // np.exp(-(dists**2) / 2.0)
+    }
+}
+
+// k = c0 + c1 * f : ConstantKernel * stat (c0 = 0), stat alone (c1 = 1), ConstantKernel + stat (c1 = 1)
+__device__ __forceinline__ double affine(double c0, double c1, double f) {
+    return __dadd_rn(c0, __dmul_rn(c1, f));
+}
+
+}  // namespace bk

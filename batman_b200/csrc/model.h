@@ -1,0 +1,41 @@
+// Host-side model handle behind the C ABI (include/batman_b200.h).
+#pragma once
+#include <vector>
+
+#include "../../include/batman_b200.h"
+
+namespace bk {
+
+constexpr int MAX_P = 32;        // largest padded input dimension with an instantiated kernel
+constexpr int TILE_T = 128;      // test points per DMMA column tile
+constexpr int TILE_M = 128;      // rows of W per DMMA row panel
+constexpr int TILE_K = 16;       // train points per staged K slab
+constexpr int TILE_DOUBLES = TILE_M * TILE_K;   // 2048 doubles = 16 KiB per packed tile
+
+struct GpOutput {
+    int kind = -1;
+    double c0 = 0, c1 = 1, kdiag = 1, y_mean = 0, y_std = 1;
+    double ls[MAX_P];
+    const double* xs = nullptr;      // n_pad x P   (X_train / ls, zero padded)
+    const double* alpha = nullptr;   // n_pad       (zero padded)
+    const double* wt = nullptr;      // packed L^-1 tiles, or null
+};
+
+}  // namespace bk
+
+struct bk_gp_s {
+    int n = 0, p = 0, P = 0, m = 0, n_pad = 0;
+    double scale[bk::MAX_P];
+    double mn[bk::MAX_P];
+    std::vector<bk::GpOutput> out;
+};
+
+namespace bk {
+inline int padded_dim(int p) {
+    const int sizes[] = {2, 4, 6, 8, 10, 12, 16, 20, 24, 32};
+    for (int s : sizes)
+        if (p <= s) return s;
+    return -1;
+}
+inline int padded_n(int n) { return (n + TILE_M - 1) / TILE_M * TILE_M; }
+}  // namespace bk

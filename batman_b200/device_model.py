@@ -1,0 +1,142 @@
+"""Device-resident state of a fitted Kriging model (m independent GPs, one design).
+
+Holds torch CUDA tensors (plumbing: device memory + streams) and the opaque
+C handle; every computation goes through the C ABI.  Data layout in HBM, per
+output q (DESIGN.md §"Data layout"):
+
+* ``xs[q]``     (n_pad, P) float64   X_train / length_scale, zero padded
+* ``alpha[q]``  (n_pad,)   float64   K^-1 y (sklearn ``alpha_``), zero padded
+* ``wt[q]``     (n_pad*n_pad,) float64  L^-1 packed in DMMA-fragment tiles
+                (built lazily: only sigma needs it)
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def current_stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DeviceModel:
+    def __init__(self, X, specs, alphas, Ls, y_means, y_stds, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("batman_b200 needs a CUDA device: there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else 'cuda:%d' % torch.cuda.current_device())
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        self.n, self.p = X.shape
+        self.m = len(specs)
+        self.P = self.lib.bk_gp_padded_dim(self.p)
+        if self.P < 0:
+            raise NotImplementedError("input dimension %d has no instantiated device kernel (max 32)" % self.p)
+        self.n_pad = self.lib.bk_gp_padded_n(self.n)
+        self.specs = specs
+        self._Ls = Ls                    # host copies; W is built from them on first sigma request
+        self.y_means = [float(v) for v in y_means]
+        self.y_stds = [float(v) for v in y_stds]
+        handle = ctypes.c_void_p()
+        _lib.check(self.lib.bk_gp_create(ctypes.byref(handle), self.n, self.p, self.m))
+        self.handle = handle
+        with torch.cuda.device(self.device):
+            Xd = torch.from_numpy(X).to(self.device)
+            self.xs, self.alpha, self.wt = [], [], [None] * self.m
+            for q, spec in enumerate(specs):
+                ls = torch.from_numpy(np.asarray(spec.ls, dtype=np.float64)).to(self.device)
+                xs = torch.zeros((self.n_pad, self.P), dtype=torch.float64, device=self.device)
+                xs[:self.n, :self.p] = Xd / ls            # IEEE division, same bits as numpy's X / length_scale
+                al = torch.zeros(self.n_pad, dtype=torch.float64, device=self.device)
+                al[:self.n] = torch.from_numpy(np.ascontiguousarray(alphas[q], dtype=np.float64).ravel()).to(self.device)
+                self.xs.append(xs)
+                self.alpha.append(al)
+                self._set_output(q)
+        self._workspace = None
+        self._scaler = None
+
+    # -- C handle ------------------------------------------------------------------------------
+    def _set_output(self, q):
+        spec = self.specs[q]
+        _lib.check(self.lib.bk_gp_set_output(
+            self.handle, q, spec.kind, spec.c0, spec.c1, spec.kdiag, _lib.as_double_array(spec.ls),
+            _ptr(self.xs[q]), _ptr(self.alpha[q]), _ptr(self.wt[q]), self.y_means[q], self.y_stds[q]))
+
+    def set_scaler(self, scale, mn):
+        """MinMaxScaler fused into the kernels (surrogate_model.py:181); None = identity."""
+        if scale is None:
+            _lib.check(self.lib.bk_gp_set_scaler(self.handle, None, None))
+        else:
+            _lib.check(self.lib.bk_gp_set_scaler(self.handle, _lib.as_double_array(scale), _lib.as_double_array(mn)))
+        self._scaler = (scale, mn)
+
+    def ensure_w(self):
+        """W = L^-1 (once per model), packed into DMMA fragment tiles by bk_pack_w."""
+        if all(w is not None for w in self.wt):
+            return
+        if self._Ls is None:
+            raise RuntimeError("sigma requested but the model holds no Cholesky factor")
+        with torch.cuda.device(self.device):
+            eye = torch.eye(self.n, dtype=torch.float64, device=self.device)
+            for q in range(self.m):
+                if self.wt[q] is not None:
+                    continue
+                L = torch.from_numpy(np.ascontiguousarray(self._Ls[q], dtype=np.float64)).to(self.device)
+                # one-off upload step (plain library TRSM); the per-point forward substitution of the
+                # reference (sklearn:_gpr.py:460) is what the hand-written DMMA kernel replaces
+                W = torch.linalg.solve_triangular(L, eye, upper=False).contiguous()
+                wt = torch.empty(self.lib.bk_gp_wtiles_len(self.n), dtype=torch.float64, device=self.device)
+                _lib.check(self.lib.bk_pack_w(_ptr(W), self.n, _ptr(wt), current_stream_ptr()))
+                torch.cuda.current_stream().synchronize()
+                self.wt[q] = wt
+                self._set_output(q)
+
+    def close(self):
+        if getattr(self, 'handle', None) is not None and self.handle.value:
+            self.lib.bk_gp_destroy(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- compute -------------------------------------------------------------------------------
+    def workspace(self, k, want_std):
+        need = self.lib.bk_gp_predict_workspace(self.handle, k, 1 if want_std else 0)
+        if need == 0:
+            return None, 0
+        if self._workspace is None or self._workspace.numel() * 8 < need:
+            self._workspace = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
+        return self._workspace, self._workspace.numel() * 8
+
+    def predict_device(self, pts_dev, return_std=True):
+        """pts_dev: (k, p) float64 CUDA tensor -> (mean, std) CUDA tensors (k, m); std None if not requested."""
+        k = pts_dev.shape[0]
+        mean = torch.empty((k, self.m), dtype=torch.float64, device=self.device)
+        std = torch.empty((k, self.m), dtype=torch.float64, device=self.device) if return_std else None
+        if k == 0:
+            return mean, std
+        if return_std:
+            self.ensure_w()
+        ws, ws_bytes = self.workspace(k, return_std)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.bk_gp_predict(self.handle, _ptr(pts_dev), k, _ptr(mean), _ptr(std), _ptr(ws),
+                                              ws_bytes, current_stream_ptr()))
+        return mean, std
+
+    def predict(self, points, return_std=True):
+        """numpy in, numpy out (the Kriging.evaluate boundary): host<->device copies included."""
+        points = np.ascontiguousarray(points, dtype=np.float64)
+        with torch.cuda.device(self.device):
+            pts = torch.from_numpy(points).to(self.device, non_blocking=False)
+            mean, std = self.predict_device(pts, return_std)
+            mean = mean.cpu().numpy()
+            std = std.cpu().numpy() if std is not None else None
+        return mean, std

@@ -1,0 +1,237 @@
+"""``UQ.sobol()`` drop-in (uq/uq.py:79-185, 192-218, 286-499 of the reference).
+
+The reference draws a Saltelli experiment with OpenTURNS, evaluates the
+surrogate on its N(2p+2) rows one point at a time and hands the outputs to
+``ot.SaltelliSensitivityAlgorithm``.  Here the three steps are one device pass:
+base rows are generated in-kernel (or supplied), predicted, multiplied into the
+estimator's sums and reduced, so neither the design nor the outputs are stored.
+
+Return value and conventions are the reference's: ``sobol()`` returns
+``[S2, S1, ST]`` -- aggregated over the outputs for ``indices='aggregated'``
+(uq.py:400-436), of the trapz-integrated output for ``'block'`` (uq.py:319-324,
+466-468).  Estimator conventions: oracle/saltelli.py header (OpenTURNS itself
+is not installable here: parity with OT's numbers is unpinned, parity with the
+restated estimator is tested to 1e-8).
+
+Base rows shard across ranks when ``torch.distributed`` is initialised: rank g
+takes rows [g N/G, (g+1) N/G), the per-rank (hi, lo) sums are summed with ONE
+all-reduce, every rank finalises.
+"""
+import ctypes
+import logging
+
+import numpy as np
+
+from . import _lib, distributions
+
+
+class UQ:
+    """Uncertainty Quantification class (Sobol' part)."""
+
+    logger = logging.getLogger(__name__)
+
+    def __init__(self, surrogate, dists=None, nsample=1000, method='sobol', indices='aggregated', space=None,
+                 data=None, plabels=None, xlabel=None, flabel=None, xdata=None, fname=None, test=None, mesh={},
+                 seed=123456, base_samples=None):
+        """Arguments as uq.py:79-119.  Two additions, both keyword-only in spirit:
+
+        :param int seed: seed of the counter-based base-sample generator
+          (batman seeds OpenTURNS with 123456, batman/__init__.py:6).
+        :param base_samples: optional ``(A, B)`` arrays (nsample, p) to use instead
+          of the generator (any distribution, any RNG).
+        """
+        self.logger.info("\n----- UQ module -----")
+        self.test = test
+        self.fname = fname
+        self.xlabel = xlabel
+        self.flabel = flabel
+        self.mesh_kwargs = mesh
+        self.surrogate = surrogate
+        self.p_len = len(dists)
+        self.plabels = ["x" + str(i) for i in range(self.p_len)] if plabels is None else plabels
+        self.method_sobol = method
+        self.type_indices = indices
+        self.space = space
+        self.points_sample = nsample
+        self.seed = int(seed)
+        self.base_samples = base_samples
+        self.dists = dists
+        if base_samples is None or surrogate is None:
+            try:
+                self.marg_kinds, self.marg_params = distributions.parse_all(dists)
+            except SystemError:
+                self.logger.error('OpenTURNS distribution unknown.')
+                raise
+        else:
+            self.marg_kinds, self.marg_params = [0] * self.p_len, [0.0, 1.0] * self.p_len
+        if self.surrogate is not None:
+            if self.surrogate.pod is not None:
+                self.output_len = int(self.surrogate.pod.mean_snapshot.shape[0])
+            else:
+                self.output_len = int(self.surrogate.predictor.model_len)
+            self.init_size = self.surrogate.space.doe_init
+        else:                                                            # ensemble mode, uq.py:175-180
+            self.init_size = len(space)
+            data = np.asarray(data, dtype=np.float64)
+            self.output_len = data.shape[1]
+            self.output = data
+            self.points_sample = self.init_size
+        if (xdata is None) and (self.output_len > 1):
+            self.xdata = np.linspace(0, 1, self.output_len)
+        else:
+            self.xdata = xdata
+        self.details = None
+
+    def __repr__(self):
+        return ("UQ object: Method({}), Input({}), Distribution({})"
+                .format(self.method_sobol, self.plabels, self.dists))
+
+    # ------------------------------------------------------------------ surrogate evaluation
+    def func(self, coords):
+        """Surrogate mean at raw points: (n, output_len) (uq.py:192-203)."""
+        f_eval, _ = self.surrogate(np.atleast_2d(coords))
+        return f_eval
+
+    def int_func(self, coords):
+        """Trapezoidal integral of the surrogate mean along the output (uq.py:205-218)."""
+        f_eval = self.func(coords)
+        return ((f_eval[:, 1:] + f_eval[:, :-1]) / 2.0).sum(axis=1)[:, None]
+
+    # ------------------------------------------------------------------ Sobol'
+    def sobol(self):
+        """Compute Sobol' indices: returns [second, first, total] (uq.py:286-499)."""
+        import torch
+        import torch.distributed as dist
+        if self.method_sobol != 'sobol':
+            raise NotImplementedError("method %r: only the Saltelli 'sobol' path is accelerated" % self.method_sobol)
+        if not torch.cuda.is_available():
+            raise RuntimeError("batman_b200.UQ.sobol needs a CUDA device: there is no CPU fallback")
+        self.logger.info("\n----- Sobol' indices -----")
+        lib = _lib.load()
+        p = self.p_len
+        block = self.type_indices == 'block'
+        F = 1 if block else self.output_len
+        second = 1
+        nsums = lib.bk_sobol_nsums(p, second)
+        nslots = lib.bk_sobol_nslots()
+        nb = 2 * p + 2 if p > 2 else p + 2
+        dev = torch.device('cuda', torch.cuda.current_device())
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        partials = torch.zeros((nslots, F, nsums, 2), dtype=torch.float64, device=dev)
+        world, rank = 1, 0
+        if self.surrogate is not None and dist.is_available() and dist.is_initialized():
+            world, rank = dist.get_world_size(), dist.get_rank()
+
+        def ptr(t):
+            return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+        if self.surrogate is not None:
+            size = int(self.points_sample)
+            lo, hi = rank * size // world, (rank + 1) * size // world
+            kinds = _lib.as_int_array(self.marg_kinds)
+            params = _lib.as_double_array(self.marg_params)
+            A_all = B_all = None
+            if self.base_samples is not None:
+                A_all = torch.from_numpy(np.ascontiguousarray(self.base_samples[0], dtype=np.float64)).to(dev)
+                B_all = torch.from_numpy(np.ascontiguousarray(self.base_samples[1], dtype=np.float64)).to(dev)
+                if A_all.shape != (size, p) or B_all.shape != (size, p):
+                    raise ValueError("base_samples must be two (nsample, p) arrays")
+            model = self.surrogate.predictor._model()
+            pod = self.surrogate.pod
+            if pod is None and not block:
+                # fused path: design -> mean -> products -> (hi, lo) sums, nothing stored
+                self.surrogate.predictor.set_input_scaler(self.surrogate.scaler.scale_, self.surrogate.scaler.min_)
+                shift = _lib.as_double_array(model.y_means)
+                _lib.check(lib.bk_sobol_accumulate(
+                    model.handle, ptr(A_all[lo:hi]) if A_all is not None else None,
+                    ptr(B_all[lo:hi]) if B_all is not None else None, self.seed, kinds, params, lo, hi - lo,
+                    second, shift, ptr(partials), stream))
+            else:
+                # POD field / block integral: modes are predicted chunk-wise, lifted to the field and
+                # reduced by the HBM-bound reducer (Y never exceeds one chunk)
+                ymean = torch.tensor(model.y_means, dtype=torch.float64, device=dev)[None, :]
+                shift_f = pod.inverse_transform_device(ymean)[0] if pod is not None else ymean[0]
+                if block:
+                    shift_f = ((shift_f[1:] + shift_f[:-1]) / 2.0).sum()[None]
+                shift_f = shift_f.contiguous()
+                chunk = max(1, min(hi - lo, int((1 << 28) // max(1, nb * self.output_len))))
+                for c0 in range(lo, hi, chunk):
+                    cnt = min(chunk, hi - c0)
+                    if A_all is not None:
+                        A, B = A_all[c0:c0 + cnt], B_all[c0:c0 + cnt]
+                    else:
+                        A = torch.empty((cnt, p), dtype=torch.float64, device=dev)
+                        B = torch.empty((cnt, p), dtype=torch.float64, device=dev)
+                        _lib.check(lib.bk_design_rows(self.seed, c0, cnt, p, kinds, params, 0, ptr(A), stream))
+                        _lib.check(lib.bk_design_rows(self.seed, c0, cnt, p, kinds, params, 1, ptr(B), stream))
+                    D = self._design_blocks(A, B, nb)
+                    Y, _ = self.surrogate.predict_device(D.view(nb * cnt, p), return_std=False)
+                    if block:
+                        Y = ((Y[:, 1:] + Y[:, :-1]) / 2.0).sum(dim=1, keepdim=True)
+                    Y = Y.contiguous()
+                    _lib.check(lib.bk_sobol_accumulate_y(ptr(Y), cnt, cnt, p, F, second, ptr(shift_f),
+                                                         ptr(partials), stream))
+            self.logger.info("Created {} samples for Sobol'".format(nb * size))
+        else:
+            # ensemble mode (uq.py:336-339): user-supplied Saltelli output sample
+            size = len(self.space) // (2 * p + 2)
+            nb_given = 2 * p + 2
+            Y = torch.from_numpy(np.ascontiguousarray(self.output[:nb_given * size], dtype=np.float64)).to(dev)
+            if block:
+                Y = ((Y[:, 1:] + Y[:, :-1]) / 2.0).sum(dim=1, keepdim=True).contiguous()
+            shift_f = Y[:size].mean(dim=0).contiguous()
+            _lib.check(lib.bk_sobol_accumulate_y(ptr(Y), size, size, p, F, second, ptr(shift_f), ptr(partials),
+                                                 stream))
+
+        totals = torch.empty((F, nsums, 2), dtype=torch.float64, device=dev)
+        _lib.check(lib.bk_sobol_reduce_slots(ptr(partials), F, nsums, ptr(totals), stream))
+        if world > 1:
+            dist.all_reduce(totals, op=dist.ReduceOp.SUM)       # the path's only collective
+        out = torch.empty(lib.bk_sobol_result_len(p, F), dtype=torch.float64, device=dev)
+        _lib.check(lib.bk_sobol_finalize(ptr(totals), size, p, F, second, ptr(out), stream))
+        res = out.cpu().numpy()
+        self.details = self._unpack(res, p, F)
+        d = self.details
+        self.logger.debug("-> Second order:\n{}\n".format(d['S2']))
+        self.logger.debug("-> First order:\n{}\n-> Total:\n{}\n".format(d['S1'], d['ST']))
+        if self.type_indices == 'aggregated':
+            aggregated = [d['S2_agg'], d['S1_agg'], d['ST_agg']]
+            self.logger.info("Aggregated_indices:\n-> Second order:\n{}\n-> First order:\n{}\n-> Total order:\n{}\n"
+                             .format(*aggregated))
+        else:
+            aggregated = [d['S2'][0], d['S1'][0], d['ST'][0]]            # uq.py:466-468
+            self.xdata = None
+        return aggregated
+
+    @staticmethod
+    def _design_blocks(A, B, nb):
+        """[A; B; E^1..E^p; (C^1..C^p)] as a (nb, cnt, p) tensor (SobolIndicesExperiment layout)."""
+        import torch
+        cnt, p = A.shape
+        D = torch.empty((nb, cnt, p), dtype=torch.float64, device=A.device)
+        D[0], D[1] = A, B
+        for i in range(p):
+            D[2 + i] = A
+            D[2 + i][:, i] = B[:, i]
+        if nb == 2 * p + 2:
+            for i in range(p):
+                D[2 + p + i] = B
+                D[2 + p + i][:, i] = A[:, i]
+        return D
+
+    @staticmethod
+    def _unpack(res, p, F):
+        o = 0
+
+        def take(shape):
+            nonlocal o
+            n = int(np.prod(shape))
+            v = res[o:o + n].reshape(shape)
+            o += n
+            return v
+        d = {}
+        d['S1'], d['ST'], d['S2'] = take((F, p)), take((F, p)), take((F, p, p))
+        d['V1'], d['VT'], d['var'], d['output_var'] = take((F, p)), take((F, p)), take((F,)), take((F,))
+        d['S1_jansen'], d['ST_jansen'] = take((F, p)), take((F, p))
+        d['S1_agg'], d['ST_agg'], d['S2_agg'] = take((p,)), take((p,)), take((p, p))
+        return d

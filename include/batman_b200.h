@@ -1,0 +1,122 @@
+/*
+ * batman_b200 -- C ABI of the B200-native Kriging-over-Saltelli -> Sobol' hot path.
+ *
+ * The reference (tupui/batman 1.9) is pure Python and has no FFI of its own;
+ * its boundary for this path is two Python classes.  Each entry point below
+ * names the reference call site it replaces (paths relative to the reference
+ * root; "sklearn:" = site-packages/sklearn/gaussian_process/ of 1.9.0).
+ * INTEGRATION.md shows the ctypes binding a batman maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch types.
+ *   - every function returns 0 on success, non-zero on error; the message is
+ *     in bk_last_error() (thread-local).  Nothing throws.
+ *   - "_dev" pointers are device memory owned by the caller (torch tensors in
+ *     the Python host); "_host" pointers are host memory read during the call.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - all arithmetic is IEEE binary64.
+ */
+#ifndef BATMAN_B200_H
+#define BATMAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bk_gp_s* bk_gp_t;
+
+/* stationary factor of the covariance, sklearn:kernels.py:1723-1730, 1557-1563 */
+enum bk_kind {
+    BK_MATERN12 = 0,  /* exp(-r)                                   Matern(nu=0.5) */
+    BK_MATERN32 = 1,  /* (1 + sqrt3 r) exp(-sqrt3 r)               Matern(nu=1.5), batman default kriging.py:85-88 */
+    BK_MATERN52 = 2,  /* (1 + sqrt5 r + 5r^2/3) exp(-sqrt5 r)      Matern(nu=2.5) */
+    BK_RBF = 3,       /* exp(-0.5 r^2) on the squared distance     RBF */
+    BK_MATERN_INF = 4 /* exp(-(r*r)/2) on the rooted distance      Matern(nu=inf) */
+};
+
+enum bk_marginal_kind { BK_UNIFORM = 0, BK_NORMAL = 1 };
+
+int bk_version(void);
+const char* bk_last_error(void);
+int bk_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* Optional per-kernel timing with CUDA events on the launching stream (bench.py roofline numbers).
+ * Categories: 0 = gp_kstar_mean (K1), 1 = gp_var_trmm (K2), 2 = fused Saltelli (K1+K3+K6),
+ * 3 = Saltelli reducer over supplied outputs, 4 = everything else.  bk_profile_read synchronises,
+ * returns the summed milliseconds and launch counts since the last read (arrays of 8) and clears. */
+int bk_profile_enable(int on);
+int bk_profile_read(double* ms_by_cat, long* launches_by_cat);
+
+/* ---- model state: replaces the fitted attributes of the m GaussianProcessRegressor
+ *      objects held in Kriging.gp_models (kriging.py:148; sklearn:_gpr.py:349-367) ---- */
+int bk_gp_create(bk_gp_t* out, int n_train, int p, int m);
+int bk_gp_destroy(bk_gp_t h);
+/* padded input dimension the kernels are instantiated for (xs_dev row pitch) */
+int bk_gp_padded_dim(int p);
+/* padded training size (multiple of 128) used by the packed L^-1 tiles */
+int bk_gp_padded_n(int n_train);
+/* doubles in the packed tile image of one n_train x n_train lower-triangular W = L^-1 */
+size_t bk_gp_wtiles_len(int n_train);
+/* output q:  k(x, x') = c0 + c1 * stat_kind(||(x - x')/ls||),  kdiag = kernel_.diag(x)
+ * (WhiteKernel noise included).  xs_dev = X_train / ls, row-major n x P, zero padded.
+ * w_tiles_dev may be NULL if sigma is never requested. */
+int bk_gp_set_output(bk_gp_t h, int q, int kind, double c0, double c1, double kdiag,
+                     const double* ls_host, const double* xs_dev, const double* alpha_dev,
+                     const double* w_tiles_dev, double y_mean, double y_std);
+/* MinMaxScaler of SurrogateModel (surrogate_model.py:108-109,181): x' = x*scale + min.
+ * NULL, NULL = identity (Kriging.evaluate receives already-scaled points). */
+int bk_gp_set_scaler(bk_gp_t h, const double* scale_host, const double* min_host);
+
+/* row-major lower-triangular W (n x n) -> packed DMMA-fragment tiles (bk_gp_wtiles_len doubles) */
+int bk_pack_w(const double* w_dev, int n_train, double* w_tiles_dev, void* stream);
+
+/* workspace (bytes) bk_gp_predict needs for k points when sigma is requested */
+size_t bk_gp_predict_workspace(bk_gp_t h, long k, int want_std);
+/* Kriging.evaluate (kriging.py:192-214) == gp.predict(return_std=True) per output
+ * (sklearn:_gpr.py:444-500), batched: pts_dev k x p row-major -> mean_dev, std_dev k x m
+ * row-major.  std_dev may be NULL (mean only). */
+int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, double* std_dev,
+                  void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- Saltelli experiment + estimator: replaces ot.SobolIndicesExperiment(...).generate(),
+ *      UQ.func over the design, and ot.SaltelliSensitivityAlgorithm (uq/uq.py:331-349,367-375) ---- */
+/* number of accumulated sums per output for input dimension p */
+int bk_sobol_nsums(int p, int second_order);
+/* number of per-CTA partial slots the accumulate kernel writes */
+int bk_sobol_nslots(void);
+/* Counter-based base samples (Philox4x32-10; oracle/philox.py is the CPU statement):
+ * rows [row_lo, row_lo+count) of stream 0 (A) or 1 (B) -> out_dev count x p. */
+int bk_design_rows(uint64_t seed, long row_lo, long count, int p, const int* marg_kind_host,
+                   const double* marg_par_host, int stream_id, double* out_dev, void* stream);
+/* Predict the surrogate mean on the Saltelli blocks [A;B;E^i;(C^i)] of base rows
+ * [row_lo, row_lo+count) and ADD the compensated sums into partials_dev
+ * ([nslots][m][nsums][2] doubles, zero it before the first call).
+ * a_dev/b_dev: explicit base samples (count x p) or NULL to generate in-kernel.
+ * shift_host: m pilot shifts subtracted before products (any value; the GP's y_mean is free). */
+int bk_sobol_accumulate(bk_gp_t h, const double* a_dev, const double* b_dev, uint64_t seed,
+                        const int* marg_kind_host, const double* marg_par_host, long row_lo,
+                        long count, int second_order, const double* shift_host,
+                        double* partials_dev, void* stream);
+/* Same sums from a user-supplied output sample (ensemble mode, uq.py:336-339):
+ * y_dev is the block-major (nblocks*N) x F output design restricted to base rows
+ * [row_lo,row_lo+count): element (block b, row k, feature f) at y_dev[(b*ld_block + k)*F + f]. */
+int bk_sobol_accumulate_y(const double* y_dev, long ld_block, long count, int p, int F,
+                          int second_order, const double* shift_dev, double* partials_dev,
+                          void* stream);
+/* fixed-order reduction of the slots: totals_dev [F][nsums][2] (this is what is all-reduced) */
+int bk_sobol_reduce_slots(const double* partials_dev, int F, int nsums, double* totals_dev, void* stream);
+/* doubles in the packed result of bk_sobol_finalize */
+size_t bk_sobol_result_len(int p, int F);
+/* Estimators from the totals.  out_dev layout (row-major, all double):
+ *   S1[F][p] ST[F][p] S2[F][p][p] V1[F][p] VT[F][p] var[F] outvar[F] J1[F][p] JT[F][p]
+ *   S1agg[p] STagg[p] S2agg[p][p] */
+int bk_sobol_finalize(const double* totals_dev, long N, int p, int F, int second_order,
+                      double* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BATMAN_B200_H */

@@ -47,3 +47,52 @@ GP_CASES = ['kriging_docstring', 'kernel_iso_matern_noise', 'kernel_iso_matern_n
 @pytest.fixture(scope='session')
 def golden():
     return load_golden
+
+
+def tree_to_sklearn(tree):
+    """oracle kernel tree -> sklearn kernel object (what the reference hands to Kriging)."""
+    from sklearn.gaussian_process import kernels as sk
+    tag = tree[0]
+    if tag == 'const':
+        return sk.ConstantKernel(tree[1])
+    if tag == 'white':
+        return sk.WhiteKernel(tree[1])
+    if tag == 'matern':
+        ls = tree[2]
+        return sk.Matern(length_scale=float(ls[0]) if len(ls) == 1 else ls, nu=tree[1])
+    if tag == 'rbf':
+        ls = tree[1]
+        return sk.RBF(length_scale=float(ls[0]) if len(ls) == 1 else ls)
+    if tag == 'sum':
+        return sk.Sum(tree_to_sklearn(tree[1]), tree_to_sklearn(tree[2]))
+    return sk.Product(tree_to_sklearn(tree[1]), tree_to_sklearn(tree[2]))
+
+
+class StateGP:
+    """Duck of a fitted GaussianProcessRegressor built from an oracle state."""
+
+    def __init__(self, st):
+        self.kernel_ = tree_to_sklearn(st['tree'])
+        self.X_train_ = st['X_train']
+        self.alpha_ = st['alpha']
+        self.L_ = st['L']
+        self._y_train_mean = st['y_mean']
+        self._y_train_std = st['y_std']
+
+
+def kriging_from_states(states):
+    from batman_b200 import Kriging
+    return Kriging.from_state([StateGP(s) for s in states])
+
+
+def synthetic_state(n, p, kind='matern32', ls=None, seed=0, func=None, c=1.5):
+    """Deterministic fixed-theta model (no optimiser): Halton design, G-function data."""
+    from oracle import functions as ofun
+    from oracle import gp as ogp
+    X = ofun.halton(n, p)
+    y = (func or ofun.g_function)(X)[:, 0]
+    ls = np.full(p, 0.7) if ls is None else np.asarray(ls, dtype=np.float64)
+    stat = {'matern32': ('matern', 1.5, ls), 'matern52': ('matern', 2.5, ls), 'matern12': ('matern', 0.5, ls),
+            'rbf': ('rbf', ls)}[kind]
+    tree = ('prod', ('const', c), stat)
+    return ogp.fit_state(tree, X, y)

@@ -1,0 +1,103 @@
+"""CPU: host-side logic and the C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+from sklearn.gaussian_process import kernels as sk
+
+from conftest import ROOT
+from batman_b200 import _lib, distributions, kernel_spec
+from batman_b200.surrogate_model import MinMax
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'batman_b200.h')).read()
+    declared = set(re.findall(r'\b(bk_[a-z_0-9]+)\s*\(', header))
+    assert declared, "no declarations parsed"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "libbatman_b200.so does not export %s" % name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+
+
+def test_library_host_only_queries():
+    lib = _lib.load()
+    assert lib.bk_version() >= 100
+    assert lib.bk_gp_padded_dim(3) == 4 and lib.bk_gp_padded_dim(8) == 8 and lib.bk_gp_padded_dim(33) == -1
+    assert lib.bk_gp_padded_n(100) == 128 and lib.bk_gp_padded_n(1024) == 1024
+    assert lib.bk_sobol_nsums(3, 1) == 5 + 18 + 6 + 3
+    assert lib.bk_sobol_nsums(2, 1) == 5 + 12           # p == 2: C blocks are E blocks
+    assert lib.bk_sobol_nsums(8, 0) == 5 + 48
+    h = ctypes.c_void_p()
+    assert lib.bk_gp_create(ctypes.byref(h), 10, 40, 1) != 0      # p too large: error, not a crash
+    assert b'dimension' in lib.bk_last_error()
+    assert lib.bk_gp_create(ctypes.byref(h), 10, 3, 2) == 0
+    assert lib.bk_gp_set_output(h, 5, 1, 0.0, 1.0, 1.0, None, None, None, None, 0.0, 1.0) != 0
+    assert lib.bk_gp_destroy(h) == 0
+
+
+def test_kernel_flatten_matches_sklearn_semantics():
+    rng = np.random.RandomState(0)
+    X, Y = rng.rand(7, 3), rng.rand(5, 3)
+    cases = [
+        sk.ConstantKernel(2.5) * sk.Matern(length_scale=[0.3, 1.0, 2.0], nu=1.5),
+        sk.Matern(length_scale=0.7, nu=1.5) + sk.WhiteKernel(0.8),
+        sk.ConstantKernel(1.3) + sk.Matern(length_scale=0.5, nu=0.5) + sk.WhiteKernel(1.0),
+        sk.ConstantKernel(0.5) * sk.RBF(length_scale=[1.0, 2.0, 3.0]) + sk.WhiteKernel(1e-3),
+        sk.ConstantKernel(2.0) * sk.Matern(length_scale=1.1, nu=2.5) * sk.ConstantKernel(3.0),
+        sk.Matern(length_scale=1.1, nu=np.inf),
+    ]
+    stat = {kernel_spec.KIND_MATERN12: lambda r: np.exp(-r),
+            kernel_spec.KIND_MATERN32: lambda r: (1 + np.sqrt(3) * r) * np.exp(-np.sqrt(3) * r),
+            kernel_spec.KIND_MATERN52: lambda r: (1 + np.sqrt(5) * r + 5 * r * r / 3) * np.exp(-np.sqrt(5) * r),
+            kernel_spec.KIND_RBF: lambda r: np.exp(-0.5 * r * r),
+            kernel_spec.KIND_MATERN_INF: lambda r: np.exp(-0.5 * r * r)}
+    for k in cases:
+        spec = kernel_spec.flatten(k, 3)
+        r = np.sqrt((((X[:, None, :] - Y[None, :, :]) / spec.ls) ** 2).sum(-1))
+        np.testing.assert_allclose(spec.c0 + spec.c1 * stat[spec.kind](r), k(X, Y), rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(np.full(7, spec.kdiag), k.diag(X), rtol=1e-15)
+
+
+def test_kernel_flatten_rejects_unsupported():
+    for k in [sk.RationalQuadratic(), sk.Matern(nu=1.0), sk.DotProduct(),
+              sk.Matern(length_scale=1.0) * sk.RBF(length_scale=2.0),
+              sk.Matern(length_scale=1.0) + sk.RBF(length_scale=2.0)]:
+        with pytest.raises(NotImplementedError):
+            kernel_spec.flatten(k, 2)
+    with pytest.raises(ValueError):
+        kernel_spec.flatten(sk.Matern(length_scale=[1.0, 2.0]), 3)
+
+
+def test_distributions():
+    assert distributions.parse('Uniform(-3.1415, 3.1415)') == (0, -3.1415, 3.1415)
+    assert distributions.parse('Normal(4035., 400.)') == (1, 4035.0, 400.0)
+    assert distributions.parse(('uniform', 0, 1)) == (0, 0.0, 1.0)
+    with pytest.raises(SystemError):                 # uq.py:156-158
+        distributions.parse('Unifrom(0, 1)')
+    with pytest.raises(NotImplementedError):
+        distributions.parse('BetaMuSigma(4035, 400, 2500, 6000).getDistribution()')
+    kinds, params = distributions.parse_all(['Uniform(15., 60.)', 'Normal(4035., 400.)'])
+    assert kinds == [0, 1] and params == [15.0, 60.0, 4035.0, 400.0]
+
+
+def test_minmax_is_sklearn_minmaxscaler():
+    from sklearn.preprocessing import MinMaxScaler
+    corners = np.array([[15.0, 2500.0, -np.pi], [60.0, 6000.0, np.pi]])
+    ref = MinMaxScaler().fit(corners)
+    mine = MinMax(corners)
+    assert np.array_equal(ref.scale_, mine.scale_) and np.array_equal(ref.min_, mine.min_)
+    pts = np.random.RandomState(0).rand(50, 3) * 100
+    assert np.array_equal(ref.transform(pts), mine.transform(pts))
+
+
+def test_no_product_import_of_oracle():
+    """The product path must not route through the oracle."""
+    pkg = os.path.join(ROOT, 'batman_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f

@@ -52,6 +52,14 @@ int launch_sobol_y(const double* y, long ld_block, long count, int p, int F, int
 int launch_reduce_slots(const double* partials, int F, int nsums, double* totals, cudaStream_t st);
 int launch_finalize(const double* totals, long N, int p, int F, int second, double* out, cudaStream_t st);
 size_t sobol_result_len(int p, int F);
+size_t lml_workspace_bytes(int n, int R, bool with_wt);
+int lml_batched(const double* X, const double* y, int n, int p, int R, const int* kinds, const double* c0,
+                const double* c1, const double* kdiag, const double* ls, double* lml_out, void* ws, size_t ws_bytes,
+                cudaStream_t st);
+int gp_factorise(const double* X, const double* y, int n, int p, int kind, double c0, double c1, double kdiag,
+                 const double* ls, double* L_out, double* alpha_out, double* wt_tiles_out, double* lml_out,
+                 int* info_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int sobol_nsums_host(int p, int second);
 int sobol_nslots_host();
 
@@ -152,7 +160,7 @@ int bk_pack_w(const double* w_dev, int n, double* w_tiles_dev, void* stream) {
 size_t bk_gp_predict_workspace(bk_gp_t h, long k, int want_std) {
     if (!h || !want_std || k <= 0) return 0;
     long kk = (k + PRED_CHUNK_ALIGN - 1) / PRED_CHUNK_ALIGN * PRED_CHUNK_ALIGN;
-    const long cap = 148L * TILE_T * 4;   // 4 test tiles per SM per chunk keeps K* (n_pad * 8 B per point) L2-friendly
+    const long cap = 148L * TILE_T * 8;   // 8 test tiles per SM per chunk: 16 warps/SM for K1, 8 waves for K2
     if (kk > cap) kk = cap;
     return (size_t)kk * h->n_pad * sizeof(double);
 }
@@ -183,6 +191,35 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
         }
     }
     return 0;
+}
+
+size_t bk_lml_workspace(int n_train, int n_candidates, int with_inverse) {
+    return lml_workspace_bytes(n_train, n_candidates, with_inverse != 0);
+}
+
+int bk_lml_batched(const double* x_dev, const double* y_dev, int n_train, int p, int n_candidates,
+                   const int* kind_host, const double* c0_host, const double* c1_host, const double* kdiag_host,
+                   const double* ls_host, double* lml_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!x_dev || !y_dev || !kind_host || !c0_host || !c1_host || !kdiag_host || !ls_host || !lml_dev || !workspace_dev)
+        return set_error("bk_lml_batched: NULL pointer");
+    if (n_train < 1 || p < 1 || n_candidates < 1) return set_error("bk_lml_batched: n, p, R must be >= 1");
+    return lml_batched(x_dev, y_dev, n_train, p, n_candidates, kind_host, c0_host, c1_host, kdiag_host, ls_host,
+                       lml_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bk_gp_factorise(const double* x_dev, const double* y_dev, int n_train, int p, int kind, double c0, double c1,
+                    double kdiag, const double* ls_host, double* l_dev, double* alpha_dev, double* w_tiles_dev,
+                    double* lml_dev, int* info_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!x_dev || !y_dev || !ls_host || !l_dev || !alpha_dev || !lml_dev || !info_dev || !workspace_dev)
+        return set_error("bk_gp_factorise: NULL pointer");
+    return gp_factorise(x_dev, y_dev, n_train, p, kind, c0, c1, kdiag, ls_host, l_dev, alpha_dev, w_tiles_dev, lml_dev,
+                        info_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bk_tri_inverse_pack(const double* l_dev, int n_train, double* w_tiles_dev, void* workspace_dev,
+                        size_t workspace_bytes, void* stream) {
+    if (!l_dev || !w_tiles_dev || !workspace_dev) return set_error("bk_tri_inverse_pack: NULL pointer");
+    return tri_inverse_pack(l_dev, n_train, w_tiles_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }
 
 int bk_sobol_nsums(int p, int second_order) { return sobol_nsums_host(p, second_order); }

@@ -1,0 +1,529 @@
+// K5: batched log-marginal-likelihood (build K, blocked Cholesky, forward solve) and the
+// triangular inverse W = L^-1 that K2 consumes -- all FP64, DMMA for the O(n^3) parts.
+//
+// Replaces, per hyper-parameter candidate theta_r (kriging.py:164-171 -> sklearn:_gpr.py:584-617):
+//     K = kernel(X_train) ; K[diag] += 1e-10 ; L = cholesky(K) ; alpha = cho_solve(L, y)
+//     lml = -1/2 y.alpha - sum(log diag L) - n/2 log(2 pi)            (-inf if the Cholesky fails)
+// The reference evaluates one theta per call in forked processes; here R candidates are factorised
+// side by side (grid.y = candidate).  y.alpha = ||L^-1 y||^2, so only the forward solve is needed for
+// the LML; z = L^-1 y rides along with the factorisation, block column by block column.
+//
+// Blocked left-looking Cholesky, NB = 128, row-major n_pad x n_pad per candidate (lower triangle):
+//   for block column k:   T_ik  = A_ik - sum_{j<k} L_ij L_kj^T      (k_gemm_nt: DMMA, i >= k)
+//                         L_kk  = chol(T_kk), Winv_k = L_kk^-1       (k_chol_diag: one CTA, shared memory)
+//                         z_k   = Winv_k (y_k - L_k,<k z_<k)         (same kernel)
+//                         L_ik  = T_ik Winv_k^T                      (k_gemm_nt, i > k)
+// The same NT GEMM drives the blocked triangular inversion (computed transposed, WT = L^-T):
+//   for block column i:   S_ki  = sum_{k<=j<i} WT_kj L_ij^T ;  WT_ki = -S_ki Winv_i^T ;  WT_ii = Winv_i^T
+// Padded rows/columns carry an identity block, so log-det, z and W are unaffected.
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "covariance.cuh"
+#include "model.h"
+
+namespace bk {
+
+constexpr int NB = 128;
+constexpr double JITTER = 1e-10;   // GaussianProcessRegressor(alpha=1e-10), sklearn:_gpr.py:215
+
+// ---------------------------------------------------------------- candidate parameters (device copy)
+struct Cand {
+    int kind;
+    int pad_;
+    double c0, c1, kdiag;
+    double ls[MAX_P];
+};
+
+// ---------------------------------------------------------------- K(theta_r): lower block tiles
+__global__ void __launch_bounds__(256) k_build_K(const double* __restrict__ X, int n, int p, int n_pad,
+                                                 const Cand* __restrict__ cands, double* __restrict__ M,
+                                                 long batch_stride) {
+    extern __shared__ __align__(16) double sm[];
+    double* xr = sm;                 // [128][p]   rows of this tile, scaled
+    double* xcT = sm + NB * p;       // [p][128]   cols of this tile, scaled, transposed
+    // lower-triangular tile index -> (bi, bj), bj <= bi
+    int t = blockIdx.x, bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    const int bj = t - bi * (bi + 1) / 2;
+    const Cand& cd = cands[blockIdx.y];
+    double* Mr = M + (size_t)blockIdx.y * batch_stride;
+    for (int idx = threadIdx.x; idx < NB * p; idx += blockDim.x) {
+        const int r = idx / p, c = idx % p;
+        const int gr = bi * NB + r, gc = bj * NB + r;
+        xr[r * p + c] = gr < n ? __ddiv_rn(X[(size_t)gr * p + c], cd.ls[c]) : 0.0;     // X / length_scale
+        xcT[c * NB + r] = gc < n ? __ddiv_rn(X[(size_t)gc * p + c], cd.ls[c]) : 0.0;
+    }
+    __syncthreads();
+    const int kind = cd.kind;
+    for (int e = 0; e < NB * NB / 256; ++e) {
+        const int idx = e * 256 + threadIdx.x;
+        const int r = idx >> 7, c = idx & 127;
+        const int gr = bi * NB + r, gc = bj * NB + c;
+        double v;
+        if (gr >= n || gc >= n) {
+            v = gr == gc ? 1.0 : 0.0;                                   // identity padding
+        } else if (gr == gc) {
+            v = __dadd_rn(cd.kdiag, JITTER);                            // kernel_.diag + alpha (sklearn:_gpr.py:589)
+        } else {
+            double s = 0.0;
+            for (int d = 0; d < p; ++d) {                               // pdist order: sequential, non-fused
+                const double df = __dadd_rn(xr[r * p + d], -xcT[d * NB + c]);
+                s = __dadd_rn(s, __dmul_rn(df, df));
+            }
+            double f;
+            switch (kind) {
+                case BK_MATERN12: f = stationary<BK_MATERN12>(s); break;
+                case BK_MATERN32: f = stationary<BK_MATERN32>(s); break;
+                case BK_MATERN52: f = stationary<BK_MATERN52>(s); break;
+                case BK_RBF: f = stationary<BK_RBF>(s); break;
+                default: f = stationary<BK_MATERN_INF>(s); break;
+            }
+            v = affine(cd.c0, cd.c1, f);
+        }
+        Mr[(size_t)gr * n_pad + gc] = v;
+    }
+}
+
+// ---------------------------------------------------------------- C = beta*C + alpha * A * B^T  (row-major, DMMA)
+struct GemmArgs {
+    const double* A; long a_batch, a_tile; int lda;
+    const double* B; long b_batch, b_tile; int ldb;
+    double* C; long c_batch, c_tile; int ldc;
+    int K0, k_tile;          // K = K0 + blockIdx.x * k_tile   (multiple of 16)
+    double alpha, beta;
+};
+constexpr int G_BK = 16, G_PITCH = 20, G_STAGES = 3;     // pitch 20 doubles: conflict-free fragment loads
+constexpr size_t G_SMEM = (size_t)G_STAGES * 2 * NB * G_PITCH * 8;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256, 1) k_gemm_nt(const GemmArgs g) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 2, wn = warp & 3, gq = lane >> 2, tq = lane & 3;
+    const double* A = g.A + (size_t)blockIdx.y * g.a_batch + (size_t)blockIdx.x * g.a_tile;
+    const double* B = g.B + (size_t)blockIdx.y * g.b_batch + (size_t)blockIdx.x * g.b_tile;
+    double* C = g.C + (size_t)blockIdx.y * g.c_batch + (size_t)blockIdx.x * g.c_tile;
+    const int K = g.K0 + (int)blockIdx.x * g.k_tile;
+    const int nk = K / G_BK;
+
+    auto load_stage = [&](int s, int kb) {
+        double* As = sm + (size_t)s * 2 * NB * G_PITCH;
+        double* Bs = As + NB * G_PITCH;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int id = tid + 256 * i, row = id >> 3, ch = id & 7;
+            cp_async16(As + row * G_PITCH + ch * 2, A + (size_t)row * g.lda + kb * G_BK + ch * 2);
+            cp_async16(Bs + row * G_PITCH + ch * 2, B + (size_t)row * g.ldb + kb * G_BK + ch * 2);
+        }
+    };
+    for (int s = 0; s < G_STAGES - 1; ++s) {
+        if (s < nk) load_stage(s, s);
+        cp_async_commit();
+    }
+    double c[8][4][2];
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) c[mt][nt][0] = c[mt][nt][1] = 0.0;
+
+    for (int kb = 0; kb < nk; ++kb) {
+        cp_async_wait<G_STAGES - 2>();
+        __syncthreads();                       // stage kb landed for everyone; stage kb-1 fully consumed
+        if (kb + G_STAGES - 1 < nk) load_stage((kb + G_STAGES - 1) % G_STAGES, kb + G_STAGES - 1);
+        cp_async_commit();
+        const double* As = sm + (size_t)(kb % G_STAGES) * 2 * NB * G_PITCH;
+        const double* Bs = As + NB * G_PITCH;
+#pragma unroll
+        for (int k4 = 0; k4 < G_BK / 4; ++k4) {
+            double a[8], b[4];
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt) a[mt] = As[(wm * 64 + mt * 8 + gq) * G_PITCH + k4 * 4 + tq];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[(wn * 32 + nt * 8 + gq) * G_PITCH + k4 * 4 + tq];
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) dmma884(c[mt][nt][0], c[mt][nt][1], a[mt], b[nt]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();      // in-place use (C aliases A): every read of A is complete before any write
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const int r = wm * 64 + mt * 8 + gq, cc = wn * 32 + nt * 8 + 2 * tq;
+            double2* dst = reinterpret_cast<double2*>(C + (size_t)r * g.ldc + cc);
+            double2 v = make_double2(g.alpha * c[mt][nt][0], g.alpha * c[mt][nt][1]);
+            if (g.beta != 0.0) {
+                const double2 o = *dst;
+                v.x = fma(g.beta, o.x, v.x);
+                v.y = fma(g.beta, o.y, v.y);
+            }
+            *dst = v;
+        }
+}
+
+static int gemm_nt(const GemmArgs& g, int tiles, int batch, cudaStream_t st) {
+    if (tiles <= 0 || batch <= 0) return 0;
+    static bool attr = false;
+    if (!attr) {
+        BK_CUDA(cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
+        attr = true;
+    }
+    ProfScope prof(PROF_CHOL, st);
+    k_gemm_nt<<<dim3(tiles, batch), 256, G_SMEM, st>>>(g);
+    BK_LAUNCH_CHECK("k_gemm_nt");
+    return 0;
+}
+
+// ---------------------------------------------------------------- diagonal block: factor, invert, forward-solve
+constexpr int DP = NB + 1;   // shared pitch
+constexpr size_t DIAG_SMEM = ((size_t)NB * DP + 2 * NB) * 8;
+
+// in-place inverse of the lower-triangular matrix held in a[NB][DP] (column sweep from the right, as LAPACK dtrti2)
+__device__ void tri_invert_smem(double* a) {
+    const int tid = threadIdx.x;
+    for (int j = NB - 1; j >= 0; --j) {
+        __syncthreads();
+        const double ajj = 1.0 / a[j * DP + j];
+        double sum = 0.0;
+        const int i = tid;
+        if (i > j && i < NB) {
+            for (int cidx = j + 1; cidx <= i; ++cidx) sum = fma(a[i * DP + cidx], a[cidx * DP + j], sum);
+        }
+        __syncthreads();
+        if (i > j && i < NB) a[i * DP + j] = -sum * ajj;
+        if (tid == j) a[j * DP + j] = ajj;
+    }
+    __syncthreads();
+}
+
+// FACTOR = true : block k of the Cholesky (factor T_kk in place, Winv_k, z_k, log-det, info)
+// FACTOR = false: only Winv_k = L_kk^-1 of an already factorised matrix
+template <bool FACTOR>
+__global__ void __launch_bounds__(256, 1)
+k_diag_block(double* __restrict__ M, long m_batch, int ld, int k, double* __restrict__ Winv, long w_batch,
+             double* __restrict__ WT, long wt_batch, const double* __restrict__ y, double* __restrict__ z,
+             long z_batch, double* __restrict__ acc /* [R][2]: logdet, zz */, int* __restrict__ info) {
+    extern __shared__ __align__(16) double sm[];
+    double* a = sm;                  // [NB][DP]
+    double* sv = sm + NB * DP;       // [NB] rhs of the forward solve
+    double* zk = sv + NB;            // [NB]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = blockIdx.x;
+    double* Mr = M + (size_t)r * m_batch;
+    double* blk = Mr + (size_t)k * NB * ld + (size_t)k * NB;
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx >> 7, cidx = idx & 127;
+        a[i * DP + cidx] = cidx <= i ? blk[(size_t)i * ld + cidx] : 0.0;
+    }
+    if constexpr (FACTOR) {
+        // s = y_k - L[k, <k] z_<k : 8 warps x 16 rows, lanes stride the columns (coalesced)
+        const double* zr = z + (size_t)r * z_batch;
+        for (int i = warp * 16; i < warp * 16 + 16; ++i) {
+            const double* row = Mr + (size_t)(k * NB + i) * ld;
+            double part = 0.0;
+            for (int j = lane; j < k * NB; j += 32) part = fma(row[j], zr[j], part);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            if (lane == 0) sv[i] = y[k * NB + i] - part;
+        }
+        // unblocked right-looking Cholesky in shared memory
+        int bad = 0;
+        for (int j = 0; j < NB; ++j) {
+            __syncthreads();
+            const double d = a[j * DP + j];
+            if (!(d > 0.0) && bad == 0) bad = k * NB + j + 1;       // not positive definite (sklearn:_gpr.py:591-593)
+            const double piv = sqrt(d), inv = 1.0 / piv;
+            __syncthreads();
+            if (tid == j) a[j * DP + j] = piv;
+            if (tid > j && tid < NB) a[tid * DP + j] *= inv;
+            __syncthreads();
+            const int ti = tid >> 4, tc = tid & 15;
+            for (int i = j + 1 + ti; i < NB; i += 16) {
+                const double li = a[i * DP + j];
+                for (int cidx = j + 1 + tc; cidx <= i; cidx += 16) a[i * DP + cidx] = fma(-li, a[cidx * DP + j], a[i * DP + cidx]);
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && bad != 0 && info[r] == 0) info[r] = bad;
+        for (int idx = tid; idx < NB * NB; idx += 256) {
+            const int i = idx >> 7, cidx = idx & 127;
+            blk[(size_t)i * ld + cidx] = a[i * DP + cidx];          // L_kk (upper part zero)
+        }
+        // log-det contribution
+        double lg = tid < NB ? log(a[tid * DP + tid]) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lg += __shfl_xor_sync(0xffffffffu, lg, o);
+        if (lane == 0) zk[warp] = lg;
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 4; ++w) t += zk[w];
+            acc[2 * r] += t;
+        }
+    }
+    tri_invert_smem(a);
+    double* Wr = Winv + (size_t)r * w_batch + (size_t)k * NB * NB;
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int i = idx >> 7, cidx = idx & 127;
+        Wr[idx] = a[i * DP + cidx];
+    }
+    if (WT) {   // WT_kk = Winv_k^T into the transposed inverse
+        double* wt = WT + (size_t)r * wt_batch + (size_t)k * NB * ld + (size_t)k * NB;
+        for (int idx = tid; idx < NB * NB; idx += 256) {
+            const int i = idx >> 7, cidx = idx & 127;
+            wt[(size_t)i * ld + cidx] = a[cidx * DP + i];
+        }
+    }
+    if constexpr (FACTOR) {
+        // z_k = Winv_k s
+        if (tid < NB) {
+            double t = 0.0;
+            for (int j = 0; j <= tid; ++j) t = fma(a[tid * DP + j], sv[j], t);
+            zk[tid] = t;
+            z[(size_t)r * z_batch + k * NB + tid] = t;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double t = 0.0;
+            for (int j = 0; j < NB; ++j) t = fma(zk[j], zk[j], t);
+            acc[2 * r + 1] += t;
+        }
+    }
+}
+
+__global__ void k_lml_final(const double* __restrict__ acc, const int* __restrict__ info, int n, int R,
+                            double* __restrict__ lml) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    // -0.5 y.alpha - sum(log diag L) - n/2 log(2 pi)      (sklearn:_gpr.py:613-615)
+    const double v = -0.5 * acc[2 * r + 1] - acc[2 * r] - 0.5 * n * 1.8378770664093453;
+    lml[r] = (info[r] != 0 || !(v == v)) ? -INFINITY : v;
+}
+
+// alpha = L^-T z = WT z : one warp per row
+__global__ void k_alpha_from_wt(const double* __restrict__ WT, int ld, const double* __restrict__ z, int n_pad,
+                                double* __restrict__ alpha) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    double t = 0.0;
+    for (int j = row + lane; j < n_pad; j += 32) t = fma(WT[(size_t)row * ld + j], z[j], t);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) alpha[row] = t;
+}
+
+__global__ void k_pad_copy_lower(const double* __restrict__ L, int n, int n_pad, double* __restrict__ M) {
+    const size_t total = (size_t)n_pad * n_pad;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / n_pad), c = (int)(idx % n_pad);
+        M[idx] = (r < n && c < n) ? (c <= r ? L[(size_t)r * n + c] : 0.0) : (r == c ? 1.0 : 0.0);
+    }
+}
+
+// ---------------------------------------------------------------- host orchestration
+struct LmlWorkspace {
+    Cand* cands; double* M; double* Winv; double* z; double* acc; int* info; double* ypad;
+};
+static size_t align_up(size_t v) { return (v + 255) / 256 * 256; }
+
+size_t lml_workspace_bytes(int n, int R, bool with_wt) {
+    const size_t n_pad = padded_n(n), nP = n_pad / NB;
+    size_t b = 0;
+    b += align_up(sizeof(Cand) * R);
+    b += align_up(sizeof(double) * n_pad * n_pad * R);        // M
+    b += align_up(sizeof(double) * nP * NB * NB * R);         // Winv
+    b += align_up(sizeof(double) * n_pad * R);                // z
+    b += align_up(sizeof(double) * 2 * R);                    // acc
+    b += align_up(sizeof(int) * R);                           // info
+    b += align_up(sizeof(double) * n_pad);                    // y padded
+    if (with_wt) b += align_up(sizeof(double) * n_pad * n_pad * R);
+    return b;
+}
+static LmlWorkspace carve(void* ws, int n, int R, double** wt_out) {
+    const size_t n_pad = padded_n(n), nP = n_pad / NB;
+    char* p = (char*)ws;
+    LmlWorkspace w;
+    w.cands = (Cand*)p; p += align_up(sizeof(Cand) * R);
+    w.M = (double*)p; p += align_up(sizeof(double) * n_pad * n_pad * R);
+    w.Winv = (double*)p; p += align_up(sizeof(double) * nP * NB * NB * R);
+    w.z = (double*)p; p += align_up(sizeof(double) * n_pad * R);
+    w.acc = (double*)p; p += align_up(sizeof(double) * 2 * R);
+    w.info = (int*)p; p += align_up(sizeof(int) * R);
+    w.ypad = (double*)p; p += align_up(sizeof(double) * n_pad);
+    if (wt_out) *wt_out = (double*)p;
+    return w;
+}
+
+static int upload_cands(const LmlWorkspace& w, int R, int p, const int* kinds, const double* c0, const double* c1,
+                        const double* kdiag, const double* ls, cudaStream_t st) {
+    std::vector<Cand> h(R);
+    for (int r = 0; r < R; ++r) {
+        if (kinds[r] < BK_MATERN12 || kinds[r] > BK_MATERN_INF) return set_error("candidate %d: unknown kernel kind %d", r, kinds[r]);
+        h[r].kind = kinds[r]; h[r].pad_ = 0; h[r].c0 = c0[r]; h[r].c1 = c1[r]; h[r].kdiag = kdiag[r];
+        for (int c = 0; c < MAX_P; ++c) h[r].ls[c] = c < p ? ls[(size_t)r * p + c] : 1.0;
+    }
+    BK_CUDA(cudaMemcpyAsync(w.cands, h.data(), sizeof(Cand) * R, cudaMemcpyHostToDevice, st));
+    BK_CUDA(cudaStreamSynchronize(st));     // h goes out of scope
+    return 0;
+}
+
+// blocked Cholesky of the R matrices in w.M (in place), z and the accumulators alongside
+static int cholesky_sweep(const LmlWorkspace& w, int n, int R, double* WT, cudaStream_t st) {
+    const int n_pad = padded_n(n), nP = n_pad / NB;
+    const long mb = (long)n_pad * n_pad, wb = (long)nP * NB * NB;
+    static bool attr = false;
+    if (!attr) {
+        BK_CUDA(cudaFuncSetAttribute(k_diag_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+        BK_CUDA(cudaFuncSetAttribute(k_diag_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+        attr = true;
+    }
+    BK_CUDA(cudaMemsetAsync(w.acc, 0, sizeof(double) * 2 * R, st));
+    BK_CUDA(cudaMemsetAsync(w.info, 0, sizeof(int) * R, st));
+    for (int k = 0; k < nP; ++k) {
+        if (k > 0) {   // T_ik = A_ik - L[i, <k] L[k, <k]^T, i = k..nP-1
+            GemmArgs g;
+            g.A = w.M + (size_t)k * NB * n_pad; g.a_batch = mb; g.a_tile = (long)NB * n_pad; g.lda = n_pad;
+            g.B = w.M + (size_t)k * NB * n_pad; g.b_batch = mb; g.b_tile = 0; g.ldb = n_pad;
+            g.C = w.M + (size_t)k * NB * n_pad + (size_t)k * NB; g.c_batch = mb; g.c_tile = (long)NB * n_pad; g.ldc = n_pad;
+            g.K0 = k * NB; g.k_tile = 0; g.alpha = -1.0; g.beta = 1.0;
+            if (int rc = gemm_nt(g, nP - k, R, st)) return rc;
+        }
+        {
+            ProfScope prof(PROF_CHOL, st);
+            k_diag_block<true><<<R, 256, DIAG_SMEM, st>>>(w.M, mb, n_pad, k, w.Winv, wb, WT, mb, w.ypad, w.z, n_pad, w.acc, w.info);
+            BK_LAUNCH_CHECK("k_diag_block<true>");
+        }
+        if (k + 1 < nP) {   // L_ik = T_ik Winv_k^T, i = k+1..nP-1 (in place)
+            GemmArgs g;
+            g.A = w.M + (size_t)(k + 1) * NB * n_pad + (size_t)k * NB; g.a_batch = mb; g.a_tile = (long)NB * n_pad; g.lda = n_pad;
+            g.B = w.Winv + (size_t)k * NB * NB; g.b_batch = wb; g.b_tile = 0; g.ldb = NB;
+            g.C = const_cast<double*>(g.A); g.c_batch = mb; g.c_tile = (long)NB * n_pad; g.ldc = n_pad;
+            g.K0 = NB; g.k_tile = 0; g.alpha = 1.0; g.beta = 0.0;
+            if (int rc = gemm_nt(g, nP - k - 1, R, st)) return rc;
+        }
+    }
+    return 0;
+}
+
+// WT = L^-T (upper triangular, row-major) from L in M and the inverted diagonal blocks in Winv (WT_ii already set)
+static int trtri_sweep(const double* M, const double* Winv, double* WT, int n, cudaStream_t st) {
+    const int n_pad = padded_n(n), nP = n_pad / NB;
+    for (int i = 1; i < nP; ++i) {
+        GemmArgs g;   // S_ki = sum_{j=k}^{i-1} WT_kj L_ij^T  for k = 0..i-1   (K shrinks with k)
+        g.A = WT; g.a_batch = 0; g.a_tile = (long)NB * n_pad + NB; g.lda = n_pad;
+        g.B = M + (size_t)i * NB * n_pad; g.b_batch = 0; g.b_tile = NB; g.ldb = n_pad;
+        g.C = WT + (size_t)i * NB; g.c_batch = 0; g.c_tile = (long)NB * n_pad; g.ldc = n_pad;
+        g.K0 = i * NB; g.k_tile = -NB; g.alpha = 1.0; g.beta = 0.0;
+        if (int rc = gemm_nt(g, i, 1, st)) return rc;
+        GemmArgs h;   // WT_ki = -S_ki Winv_i^T (in place)
+        h.A = WT + (size_t)i * NB; h.a_batch = 0; h.a_tile = (long)NB * n_pad; h.lda = n_pad;
+        h.B = Winv + (size_t)i * NB * NB; h.b_batch = 0; h.b_tile = 0; h.ldb = NB;
+        h.C = WT + (size_t)i * NB; h.c_batch = 0; h.c_tile = (long)NB * n_pad; h.ldc = n_pad;
+        h.K0 = NB; h.k_tile = 0; h.alpha = -1.0; h.beta = 0.0;
+        if (int rc = gemm_nt(h, i, 1, st)) return rc;
+    }
+    return 0;
+}
+
+int launch_pack_w_ex(const double* w, int n_rows_valid, int ld, int transposed, double* out, cudaStream_t st);
+
+static int build_K(const LmlWorkspace& w, const double* X, int n, int p, int R, cudaStream_t st) {
+    const int n_pad = padded_n(n), nP = n_pad / NB;
+    const size_t smem = (size_t)2 * NB * p * 8;
+    if (smem > 48 * 1024) BK_CUDA(cudaFuncSetAttribute(k_build_K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ProfScope prof(PROF_CHOL, st);
+    k_build_K<<<dim3(nP * (nP + 1) / 2, R), 256, smem, st>>>(X, n, p, n_pad, w.cands, w.M, (long)n_pad * n_pad);
+    BK_LAUNCH_CHECK("k_build_K");
+    return 0;
+}
+
+static int stage_y(const LmlWorkspace& w, const double* y, int n, cudaStream_t st) {
+    const int n_pad = padded_n(n);
+    BK_CUDA(cudaMemsetAsync(w.ypad, 0, sizeof(double) * n_pad, st));
+    BK_CUDA(cudaMemcpyAsync(w.ypad, y, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int lml_batched(const double* X, const double* y, int n, int p, int R, const int* kinds, const double* c0,
+                const double* c1, const double* kdiag, const double* ls, double* lml_out, void* ws, size_t ws_bytes,
+                cudaStream_t st) {
+    if (p > MAX_P) return set_error("p = %d exceeds %d", p, MAX_P);
+    if (ws_bytes < lml_workspace_bytes(n, R, false))
+        return set_error("bk_lml_batched: workspace of %zu bytes needed (got %zu)", lml_workspace_bytes(n, R, false), ws_bytes);
+    LmlWorkspace w = carve(ws, n, R, nullptr);
+    if (int rc = upload_cands(w, R, p, kinds, c0, c1, kdiag, ls, st)) return rc;
+    if (int rc = stage_y(w, y, n, st)) return rc;
+    if (int rc = build_K(w, X, n, p, R, st)) return rc;
+    if (int rc = cholesky_sweep(w, n, R, nullptr, st)) return rc;
+    k_lml_final<<<(R + 127) / 128, 128, 0, st>>>(w.acc, w.info, n, R, lml_out);
+    BK_LAUNCH_CHECK("k_lml_final");
+    return 0;
+}
+
+// final state at the chosen theta: L (n_pad x n_pad, row-major lower), alpha (n_pad), packed W tiles, lml, info
+int gp_factorise(const double* X, const double* y, int n, int p, int kind, double c0, double c1, double kdiag,
+                 const double* ls, double* L_out, double* alpha_out, double* wt_tiles_out, double* lml_out,
+                 int* info_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (p > MAX_P) return set_error("p = %d exceeds %d", p, MAX_P);
+    if (ws_bytes < lml_workspace_bytes(n, 1, true))
+        return set_error("bk_gp_factorise: workspace of %zu bytes needed (got %zu)", lml_workspace_bytes(n, 1, true), ws_bytes);
+    const int n_pad = padded_n(n);
+    double* WT = nullptr;
+    LmlWorkspace w = carve(ws, n, 1, &WT);
+    if (int rc = upload_cands(w, 1, p, &kind, &c0, &c1, &kdiag, ls, st)) return rc;
+    if (int rc = stage_y(w, y, n, st)) return rc;
+    if (int rc = build_K(w, X, n, p, 1, st)) return rc;
+    BK_CUDA(cudaMemsetAsync(WT, 0, sizeof(double) * n_pad * n_pad, st));
+    if (int rc = cholesky_sweep(w, n, 1, WT, st)) return rc;
+    k_lml_final<<<1, 128, 0, st>>>(w.acc, w.info, n, 1, lml_out);
+    BK_LAUNCH_CHECK("k_lml_final");
+    BK_CUDA(cudaMemcpyAsync(info_out, w.info, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    if (int rc = trtri_sweep(w.M, w.Winv, WT, n, st)) return rc;
+    k_alpha_from_wt<<<(n_pad + 7) / 8, 256, 0, st>>>(WT, n_pad, w.z, n_pad, alpha_out);
+    BK_LAUNCH_CHECK("k_alpha_from_wt");
+    BK_CUDA(cudaMemcpyAsync(L_out, w.M, sizeof(double) * n_pad * n_pad, cudaMemcpyDeviceToDevice, st));
+    if (wt_tiles_out)
+        if (int rc = launch_pack_w_ex(WT, n_pad, n_pad, 1, wt_tiles_out, st)) return rc;
+    return 0;
+}
+
+// W tiles from a given Cholesky factor (models adopted from scikit-learn state)
+int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    if (ws_bytes < lml_workspace_bytes(n, 1, true))
+        return set_error("bk_tri_inverse_pack: workspace of %zu bytes needed (got %zu)", lml_workspace_bytes(n, 1, true), ws_bytes);
+    const int n_pad = padded_n(n), nP = n_pad / NB;
+    double* WT = nullptr;
+    LmlWorkspace w = carve(ws, n, 1, &WT);
+    static bool attr = false;
+    if (!attr) {
+        BK_CUDA(cudaFuncSetAttribute(k_diag_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
+        attr = true;
+    }
+    {
+        ProfScope prof(PROF_CHOL, st);
+        k_pad_copy_lower<<<1184, 256, 0, st>>>(L, n, n_pad, w.M);
+        BK_LAUNCH_CHECK("k_pad_copy_lower");
+    }
+    BK_CUDA(cudaMemsetAsync(WT, 0, sizeof(double) * n_pad * n_pad, st));
+    for (int k = 0; k < nP; ++k) {
+        ProfScope prof(PROF_CHOL, st);
+        k_diag_block<false><<<1, 256, DIAG_SMEM, st>>>(w.M, 0, n_pad, k, w.Winv, 0, WT, 0, nullptr, nullptr, 0, nullptr, nullptr);
+        BK_LAUNCH_CHECK("k_diag_block<false>");
+    }
+    if (int rc = trtri_sweep(w.M, w.Winv, WT, n, st)) return rc;
+    return launch_pack_w_ex(WT, n_pad, n_pad, 1, wt_tiles_out, st);
+}
+
+}  // namespace bk

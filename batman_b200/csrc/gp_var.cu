@@ -24,8 +24,9 @@
 // i.e. [m-tile 16][k8 2][lane = (r%8)*4 + j%4][2], lane.x -> j%8 < 4, lane.y -> j%8 >= 4.
 // Tile (panel, jb) sits at ((panel * n_pad/16) + jb) * 2048 doubles.
 //
-// Bound: FP64 tensor pipe.  Algorithmic flops per prediction: n_pad^2 + n_pad*128
-// (lower triangle incl. diagonal blocks, 2 flop per FMA).
+// Bound: FP64 tensor pipe.  Algorithmic flops per prediction: n^2 + 2n.  Executed: the strictly
+// lower 128x128 blocks in full, the diagonal blocks only for the 8x8 sub-blocks on or below the diagonal
+// (72 of 128 sub-steps on the busier warp row).
 #include "common.cuh"
 #include "model.h"
 
@@ -89,19 +90,28 @@ k_var_trmm(const double* __restrict__ wt, const double* __restrict__ kstar, int 
             mbar_wait(&bar[s], (step / VAR_STAGES) & 1);
             const double2* As = reinterpret_cast<const double2*>(stage + (size_t)s * 2 * TILE_DOUBLES);
             const double2* Bs = As + TILE_DOUBLES / 2;
+            // Diagonal block of the panel: W is lower triangular, so the 8x8 sub-block (m-tile, k8-step) is
+            // identically zero when its rows lie above its columns.  M-tiles are dealt to the two warp rows
+            // round-robin (m-tile = 2*mt + wm) so both carry the same share of the surviving sub-blocks.
+            const int kk8_base = (jb - panel * (TILE_M / TILE_K)) * 2;   // >= 0 only inside the diagonal block
 #pragma unroll
             for (int k8 = 0; k8 < 2; ++k8) {
+                const int kk8 = kk8_base + k8;
+                const int mt_lo = kk8 > wm ? (kk8 - wm + 1) >> 1 : 0;    // first mt with 2*mt + wm >= kk8
                 double2 a[8], b[4];
 #pragma unroll
-                for (int mt = 0; mt < 8; ++mt) a[mt] = As[(((wm * 8 + mt) * 2 + k8) * 32) + lane];
+                for (int mt = 0; mt < 8; ++mt)
+                    if (mt >= mt_lo) a[mt] = As[(((mt * 2 + wm) * 2 + k8) * 32) + lane];
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[(((wn * 4 + nt) * 2 + k8) * 32) + lane];
 #pragma unroll
                 for (int mt = 0; mt < 8; ++mt)
+                    if (mt >= mt_lo) {
 #pragma unroll
-                    for (int nt = 0; nt < 4; ++nt) {
-                        dmma884(c[mt][nt][0], c[mt][nt][1], a[mt].x, b[nt].x);
-                        dmma884(c[mt][nt][0], c[mt][nt][1], a[mt].y, b[nt].y);
+                        for (int nt = 0; nt < 4; ++nt) {
+                            dmma884(c[mt][nt][0], c[mt][nt][1], a[mt].x, b[nt].x);
+                            dmma884(c[mt][nt][0], c[mt][nt][1], a[mt].y, b[nt].y);
+                        }
                     }
             }
             __syncthreads();   // stage s fully consumed
@@ -162,7 +172,11 @@ int launch_var(const bk_gp_s* h, int q, const double* kstar, long k, double* std
 }
 
 // ---------------------------------------------------------------- packing of W
-__global__ void k_pack_w(const double* __restrict__ w, int n, int n_pad, double* __restrict__ out) {
+// src is row-major with leading dimension ld; element W[r][j] is src[r*ld + j], or src[j*ld + r] when the
+// source holds the transpose (WT = L^-T from the blocked inversion).  Entries outside the valid lower
+// triangle are written as zeros.
+__global__ void k_pack_w(const double* __restrict__ w, int n, int ld, int transposed, int n_pad,
+                         double* __restrict__ out) {
     const int njb = n_pad / TILE_K;
     const size_t total = (size_t)n_pad * n_pad;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -173,16 +187,22 @@ __global__ void k_pack_w(const double* __restrict__ w, int n, int n_pad, double*
         const int h = within & 1, tq = (within >> 1) & 3, g = (within >> 3) & 7, k8 = (within >> 6) & 1, mt = within >> 7;
         const int r = panel * TILE_M + mt * 8 + g;
         const int j = jb * TILE_K + k8 * 8 + h * 4 + tq;
-        out[idx] = (r < n && j < n && j <= r) ? w[(size_t)r * n + j] : 0.0;
+        double val = 0.0;
+        if (r < n && j < n && j <= r) val = transposed ? w[(size_t)j * ld + r] : w[(size_t)r * ld + j];
+        out[idx] = val;
     }
 }
 
-int launch_pack_w(const double* w, int n, double* out, cudaStream_t st) {
-    const int n_pad = padded_n(n);
+int launch_pack_w_ex(const double* w, int n_rows_valid, int ld, int transposed, double* out, cudaStream_t st) {
+    const int n_pad = padded_n(n_rows_valid);
     ProfScope prof(PROF_OTHER, st);
-    k_pack_w<<<1184, 256, 0, st>>>(w, n, n_pad, out);
+    k_pack_w<<<1184, 256, 0, st>>>(w, n_rows_valid, ld, transposed, n_pad, out);
     BK_LAUNCH_CHECK("k_pack_w");
     return 0;
+}
+
+int launch_pack_w(const double* w, int n, double* out, cudaStream_t st) {
+    return launch_pack_w_ex(w, n, n, 0, out, st);
 }
 
 }  // namespace bk

@@ -26,7 +26,7 @@ def current_stream_ptr():
 
 
 class DeviceModel:
-    def __init__(self, X, specs, alphas, Ls, y_means, y_stds, device=None):
+    def __init__(self, X, specs, alphas, Ls, y_means, y_stds, device=None, wts=None):
         if not torch.cuda.is_available():
             raise RuntimeError("batman_b200 needs a CUDA device: there is no CPU fallback")
         self.lib = _lib.load()
@@ -47,7 +47,8 @@ class DeviceModel:
         self.handle = handle
         with torch.cuda.device(self.device):
             Xd = torch.from_numpy(X).to(self.device)
-            self.xs, self.alpha, self.wt = [], [], [None] * self.m
+            self.xs, self.alpha = [], []
+            self.wt = list(wts) if wts is not None else [None] * self.m
             for q, spec in enumerate(specs):
                 ls = torch.from_numpy(np.asarray(spec.ls, dtype=np.float64)).to(self.device)
                 xs = torch.zeros((self.n_pad, self.P), dtype=torch.float64, device=self.device)
@@ -76,24 +77,16 @@ class DeviceModel:
         self._scaler = (scale, mn)
 
     def ensure_w(self):
-        """W = L^-1 (once per model), packed into DMMA fragment tiles by bk_pack_w."""
+        """W = L^-1 (once per model) as packed DMMA fragment tiles: blocked triangular inversion on the
+        device (bk_tri_inverse_pack), unless the fit already produced the tiles."""
         if all(w is not None for w in self.wt):
             return
         if self._Ls is None:
             raise RuntimeError("sigma requested but the model holds no Cholesky factor")
-        with torch.cuda.device(self.device):
-            eye = torch.eye(self.n, dtype=torch.float64, device=self.device)
-            for q in range(self.m):
-                if self.wt[q] is not None:
-                    continue
-                L = torch.from_numpy(np.ascontiguousarray(self._Ls[q], dtype=np.float64)).to(self.device)
-                # one-off upload step (plain library TRSM); the per-point forward substitution of the
-                # reference (sklearn:_gpr.py:460) is what the hand-written DMMA kernel replaces
-                W = torch.linalg.solve_triangular(L, eye, upper=False).contiguous()
-                wt = torch.empty(self.lib.bk_gp_wtiles_len(self.n), dtype=torch.float64, device=self.device)
-                _lib.check(self.lib.bk_pack_w(_ptr(W), self.n, _ptr(wt), current_stream_ptr()))
-                torch.cuda.current_stream().synchronize()
-                self.wt[q] = wt
+        from .lml import inverse_tiles
+        for q in range(self.m):
+            if self.wt[q] is None:
+                self.wt[q] = inverse_tiles(self._Ls[q], self.device)
                 self._set_output(q)
 
     def close(self):

@@ -110,7 +110,7 @@ def _lbfgs(obj, x0, bounds, fallback=None, h=1e-6):
 
 
 def fit_output(kernel, X_dev, X_host, y, global_optimizer, n_restarts_local):
-    """-> (kernel_, spec, alpha (n,), L (n, n), y_mean, y_std, lml_value)."""
+    """-> (kernel_, spec, alpha (n,), L (n, n), y_mean, y_std, lml_value, packed L^-1 tiles on the device)."""
     dim = X_host.shape[1]
     yn, y_mean, y_std = normalise_y(y)
     import torch
@@ -118,5 +118,5 @@ def fit_output(kernel, X_dev, X_host, y, global_optimizer, n_restarts_local):
     theta, lml_val = optimise_theta(kernel, X_dev, y_dev, dim, global_optimizer, n_restarts_local)
     kernel_ = kernel.clone_with_theta(theta)
     spec = kernel_spec.flatten(kernel_, dim)
-    L, alpha, lml_final = factorise(X_dev, y_dev, spec)
-    return kernel_, spec, alpha, L, y_mean, y_std, lml_final
+    L, alpha, lml_final, wt = factorise(X_dev, y_dev, spec)
+    return kernel_, spec, alpha, L, y_mean, y_std, lml_final, wt

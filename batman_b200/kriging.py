@@ -91,9 +91,9 @@ class Kriging:
         if not torch.cuda.is_available():
             raise RuntimeError("batman_b200.Kriging needs a CUDA device: there is no CPU fallback")
         X_dev = torch.from_numpy(np.ascontiguousarray(sample)).cuda()
-        gps, hyper = [], []
+        gps, hyper, wts = [], [], []
         for q in range(self.model_len):
-            kernel_, _, alpha, L, y_mean, y_std, lml = _fit.fit_output(
+            kernel_, _, alpha, L, y_mean, y_std, lml, wt = _fit.fit_output(
                 self.kernel, X_dev, sample, data[:, q], global_optimizer, n_local)
             hyperparameter = np.exp(kernel_.theta)                       # kriging.py:123
             if kernel is None:                                           # kriging.py:126-134
@@ -102,10 +102,12 @@ class Kriging:
                     self.logger.warning("Hyperparameters optimization not converged: {}".format(kernel_))
             gps.append(FittedGP(kernel_, sample, alpha, L, y_mean, y_std, lml))
             hyper.append(hyperparameter)
+            wts.append(wt)
         self.gp_models, self.hyperparameter = tuple(gps), tuple(hyper)   # kriging.py:148
         self.logger.debug("Kernels:\n{}".format([gp.kernel_ for gp in self.gp_models]))
         self._device = None
         self._scaler = None
+        self._wts = wts            # packed L^-1 from the fit (device tensors; dropped on pickling)
 
     # ------------------------------------------------------------------ alternate constructors
     @classmethod
@@ -129,6 +131,7 @@ class Kriging:
         self.n_restart, self.n_cpu = 1, 1
         self._device = None
         self._scaler = None
+        self._wts = None
         return self
 
     # ------------------------------------------------------------------ device state (lazy, per process)
@@ -141,7 +144,8 @@ class Kriging:
             self._device = DeviceModel(X, specs, [gp.alpha_ for gp in self.gp_models],
                                        [gp.L_ for gp in self.gp_models],
                                        [gp._y_train_mean for gp in self.gp_models],
-                                       [gp._y_train_std for gp in self.gp_models])
+                                       [gp._y_train_std for gp in self.gp_models],
+                                       wts=getattr(self, '_wts', None))
             if self._scaler is not None:
                 self._device.set_scaler(*self._scaler)
         return self._device
@@ -160,6 +164,7 @@ class Kriging:
         """dill/pickle (surrogate_model.py:271-279): numpy state only, device buffers are rebuilt lazily."""
         state = self.__dict__.copy()
         state['_device'] = None
+        state['_wts'] = None
         return state
 
     # ------------------------------------------------------------------ evaluate

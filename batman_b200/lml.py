@@ -1,80 +1,99 @@
-"""Batched log-marginal-likelihood on the device (sklearn:_gpr.py:584-617).
+"""Batched log-marginal-likelihood and final factorisation on the device (K5, csrc/chol.cu).
 
-For R candidate hyper-parameter vectors at once:
-    K_r = k_theta_r(X, X) + 1e-10 I ;  L_r = chol(K_r) ;  alpha_r = K_r^-1 y
-    LML_r = -1/2 y.alpha_r - sum(log diag L_r) - n/2 log(2 pi)     (-inf if chol fails)
+For R candidate hyper-parameter vectors at once (sklearn:_gpr.py:584-617):
+    K_r = k_theta_r(X, X) + 1e-10 I ;  L_r = chol(K_r) ;  z_r = L_r^-1 y
+    LML_r = -1/2 ||z_r||^2 - sum(log diag L_r) - n/2 log(2 pi)     (-inf if the Cholesky fails)
+All arithmetic runs in ``bk_lml_batched`` / ``bk_gp_factorise`` (hand-written blocked Cholesky on the
+FP64 tensor pipe); torch only owns the buffers.
 """
-import math
+import ctypes
 
 import numpy as np
 import torch
 
-from . import kernel_spec as ks
+from . import _lib
 
-JITTER = 1e-10          # GaussianProcessRegressor(alpha=1e-10), sklearn:_gpr.py:215
-_MAX_BATCH_BYTES = 8 << 30
-
-
-def _stat(kind, s):
-    """Same expressions as csrc/covariance.cuh, on the squared scaled distance."""
-    if kind == ks.KIND_RBF:
-        return torch.exp(-0.5 * s)
-    d = torch.sqrt(s)
-    if kind == ks.KIND_MATERN12:
-        return torch.exp(-d)
-    if kind == ks.KIND_MATERN32:
-        t = d * math.sqrt(3)
-        return (1.0 + t) * torch.exp(-t)
-    if kind == ks.KIND_MATERN52:
-        t = d * math.sqrt(5)
-        return (1.0 + t + t * t / 3.0) * torch.exp(-t)
-    return torch.exp(-(d * d) / 2.0)
+_MAX_BATCH_BYTES = 24 << 30      # matrices of one batch; candidates beyond that are processed in slices
 
 
-def build_K(X_dev, specs):
-    """(R, n, n) training covariance incl. jitter; diagonal = kernel_.diag + 1e-10 exactly."""
-    n, p = X_dev.shape
-    R = len(specs)
-    K = torch.empty((R, n, n), dtype=torch.float64, device=X_dev.device)
-    eye = torch.eye(n, dtype=torch.bool, device=X_dev.device)
-    for r, spec in enumerate(specs):
-        ls = torch.from_numpy(np.asarray(spec.ls, dtype=np.float64)).to(X_dev.device)
-        U = X_dev / ls
-        s = torch.zeros((n, n), dtype=torch.float64, device=X_dev.device)
-        for c in range(p):                       # cdist order: sequential, non-fused
-            d = U[:, c, None] - U[None, :, c]
-            s = s + d * d
-        Kr = spec.c0 + spec.c1 * _stat(spec.kind, s)
-        Kr[eye] = spec.kdiag + JITTER
-        K[r] = Kr
-    return K
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_ws_cache = {}
+
+
+def _workspace(device, nbytes):
+    buf = _ws_cache.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _ws_cache[device] = buf
+    return buf
 
 
 def lml_batched(X_dev, y_dev, specs):
-    """-> numpy (R,) of LML values; -inf where K is not numerically PD."""
-    n = X_dev.shape[0]
-    out = np.empty(len(specs))
-    per = max(1, int(_MAX_BATCH_BYTES // (3 * n * n * 8)))
-    for lo in range(0, len(specs), per):
-        K = build_K(X_dev, specs[lo:lo + per])
-        L, info = torch.linalg.cholesky_ex(K)
-        alpha = torch.cholesky_solve(y_dev[None, :, None].expand(K.shape[0], n, 1), L)[..., 0]
-        val = -0.5 * (alpha @ y_dev) - torch.log(torch.diagonal(L, dim1=1, dim2=2)).sum(dim=1) \
-            - n / 2 * math.log(2 * math.pi)
-        val = torch.where(info == 0, val, torch.full_like(val, -float('inf')))
-        out[lo:lo + per] = val.cpu().numpy()
+    """X_dev (n, p), y_dev (n,) CUDA float64 tensors; specs: list of KernelSpec -> numpy (R,) LML values."""
+    lib = _lib.load()
+    n, p = X_dev.shape
+    R = len(specs)
+    out = np.empty(R)
+    n_pad = lib.bk_gp_padded_n(n)
+    per = max(1, int(_MAX_BATCH_BYTES // (n_pad * n_pad * 8)))
+    with torch.cuda.device(X_dev.device):
+        for lo in range(0, R, per):
+            sl = specs[lo:lo + per]
+            r = len(sl)
+            ws = _workspace(X_dev.device, lib.bk_lml_workspace(n, r, 0))
+            lml = torch.empty(r, dtype=torch.float64, device=X_dev.device)
+            kinds = _lib.as_int_array([s.kind for s in sl])
+            c0 = _lib.as_double_array([s.c0 for s in sl])
+            c1 = _lib.as_double_array([s.c1 for s in sl])
+            kd = _lib.as_double_array([s.kdiag for s in sl])
+            ls = _lib.as_double_array(np.concatenate([np.asarray(s.ls, dtype=np.float64) for s in sl]))
+            _lib.check(lib.bk_lml_batched(_ptr(X_dev), _ptr(y_dev), n, p, r, kinds, c0, c1, kd, ls, _ptr(lml),
+                                          _ptr(ws), ws.numel(), _stream()))
+            out[lo:lo + r] = lml.cpu().numpy()
     return out
 
 
 def factorise(X_dev, y_dev, spec):
-    """Final state at the chosen theta (sklearn:_gpr.py:349-367): L, alpha on the host + LML."""
-    K = build_K(X_dev, [spec])[0]
-    L, info = torch.linalg.cholesky_ex(K)
-    if int(info.item()) != 0:
-        raise np.linalg.LinAlgError(
-            "The kernel is not returning a positive definite matrix. Try gradually increasing the "
-            "'alpha' parameter of your GaussianProcessRegressor estimator.")   # sklearn:_gpr.py:354-360
-    alpha = torch.cholesky_solve(y_dev[:, None], L)[:, 0]
-    n = X_dev.shape[0]
-    val = -0.5 * float(alpha @ y_dev) - float(torch.log(torch.diagonal(L)).sum()) - n / 2 * math.log(2 * math.pi)
-    return torch.tril(L).cpu().numpy(), alpha.cpu().numpy(), val
+    """Final state at the chosen theta (sklearn:_gpr.py:349-367).
+
+    -> (L (n, n) numpy lower, alpha (n,) numpy, lml float, packed L^-1 tiles as a CUDA tensor)."""
+    lib = _lib.load()
+    n, p = X_dev.shape
+    n_pad = lib.bk_gp_padded_n(n)
+    dev = X_dev.device
+    with torch.cuda.device(dev):
+        ws = _workspace(dev, lib.bk_lml_workspace(n, 1, 1))
+        L = torch.empty((n_pad, n_pad), dtype=torch.float64, device=dev)
+        alpha = torch.empty(n_pad, dtype=torch.float64, device=dev)
+        wt = torch.empty(lib.bk_gp_wtiles_len(n), dtype=torch.float64, device=dev)
+        lml = torch.empty(1, dtype=torch.float64, device=dev)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.bk_gp_factorise(_ptr(X_dev), _ptr(y_dev), n, p, spec.kind, spec.c0, spec.c1, spec.kdiag,
+                                       _lib.as_double_array(spec.ls), _ptr(L), _ptr(alpha), _ptr(wt), _ptr(lml),
+                                       _ptr(info), _ptr(ws), ws.numel(), _stream()))
+        if int(info.item()) != 0:
+            raise np.linalg.LinAlgError(
+                "The kernel is not returning a positive definite matrix. Try gradually increasing the "
+                "'alpha' parameter of your GaussianProcessRegressor estimator.")   # sklearn:_gpr.py:354-360
+        L_host = np.tril(L[:n, :n].cpu().numpy())
+        return L_host, alpha[:n].cpu().numpy(), float(lml.item()), wt
+
+
+def inverse_tiles(L_host, device):
+    """Packed L^-1 tiles from a given Cholesky factor (models adopted from scikit-learn state)."""
+    lib = _lib.load()
+    n = L_host.shape[0]
+    with torch.cuda.device(device):
+        L = torch.from_numpy(np.ascontiguousarray(L_host, dtype=np.float64)).to(device)
+        ws = _workspace(device, lib.bk_lml_workspace(n, 1, 1))
+        wt = torch.empty(lib.bk_gp_wtiles_len(n), dtype=torch.float64, device=device)
+        _lib.check(lib.bk_tri_inverse_pack(_ptr(L), n, _ptr(wt), _ptr(ws), ws.numel(), _stream()))
+        torch.cuda.current_stream().synchronize()
+    return wt

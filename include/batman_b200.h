@@ -45,7 +45,7 @@ int bk_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* Optional per-kernel timing with CUDA events on the launching stream (bench.py roofline numbers).
  * Categories: 0 = gp_kstar_mean (K1), 1 = gp_var_trmm (K2), 2 = fused Saltelli (K1+K3+K6),
- * 3 = Saltelli reducer over supplied outputs, 4 = everything else.  bk_profile_read synchronises,
+ * 3 = Saltelli reducer over supplied outputs, 4 = everything else, 5 = LML / Cholesky / inverse (K5).  bk_profile_read synchronises,
  * returns the summed milliseconds and launch counts since the last read (arrays of 8) and clears. */
 int bk_profile_enable(int on);
 int bk_profile_read(double* ms_by_cat, long* launches_by_cat);
@@ -80,6 +80,27 @@ size_t bk_gp_predict_workspace(bk_gp_t h, long k, int want_std);
  * row-major.  std_dev may be NULL (mean only). */
 int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, double* std_dev,
                   void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- hyper-parameter fit: replaces log_marginal_likelihood(theta) (sklearn:_gpr.py:584-617) as driven by
+ *      Kriging._optim_evolution / the L-BFGS-B restarts (kriging.py:99-106, 151-190), for R candidates at once,
+ *      and the final factorisation of GaussianProcessRegressor.fit (sklearn:_gpr.py:349-367). ---- */
+/* bytes of workspace for R candidates (with_inverse = 1 adds room for the triangular inverse) */
+size_t bk_lml_workspace(int n_train, int n_candidates, int with_inverse);
+/* lml_dev[r] = LML of k_r(x,x') = c0[r] + c1[r]*stat_kind[r](||(x-x')/ls[r]||), K_ii = kdiag[r] + 1e-10;
+ * -inf where the Cholesky fails.  x_dev n x p (scaled design), y_dev n (normalised targets). */
+int bk_lml_batched(const double* x_dev, const double* y_dev, int n_train, int p, int n_candidates,
+                   const int* kind_host, const double* c0_host, const double* c1_host, const double* kdiag_host,
+                   const double* ls_host /* R x p */, double* lml_dev, void* workspace_dev, size_t workspace_bytes,
+                   void* stream);
+/* Final state at one theta: l_dev (n_pad x n_pad row-major, lower triangle = L_), alpha_dev (n_pad) = alpha_,
+ * w_tiles_dev (bk_gp_wtiles_len doubles or NULL) = packed L^-1, lml_dev (1), info_dev (1; 0 = positive definite). */
+int bk_gp_factorise(const double* x_dev, const double* y_dev, int n_train, int p, int kind, double c0, double c1,
+                    double kdiag, const double* ls_host, double* l_dev, double* alpha_dev, double* w_tiles_dev,
+                    double* lml_dev, int* info_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Packed L^-1 tiles from a given Cholesky factor l_dev (n x n row-major lower), e.g. scikit-learn's L_;
+ * workspace: bk_lml_workspace(n, 1, 1). */
+int bk_tri_inverse_pack(const double* l_dev, int n_train, double* w_tiles_dev, void* workspace_dev,
+                        size_t workspace_bytes, void* stream);
 
 /* ---- Saltelli experiment + estimator: replaces ot.SobolIndicesExperiment(...).generate(),
  *      UQ.func over the design, and ot.SaltelliSensitivityAlgorithm (uq/uq.py:331-349,367-375) ---- */

@@ -1,0 +1,111 @@
+"""GPU parity: batched LML / blocked Cholesky / final factorisation (K5) vs scikit-learn.
+
+Fit parity is defined on LML(theta) at a given theta and on the fitted state at a given theta;
+the optimiser path itself is not reproducible in the reference (unseeded DE, kriging.py:170-171).
+"""
+import numpy as np
+import pytest
+from sklearn.gaussian_process import GaussianProcessRegressor
+from sklearn.gaussian_process.kernels import RBF, ConstantKernel, Matern, WhiteKernel
+
+from oracle import functions as ofun
+from oracle import gp as ogp
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n, p, seed=0):
+    X = ofun.halton(n, p)
+    y = ofun.g_function(X)[:, 0] + 0.01 * np.random.RandomState(seed).randn(n)
+    return X, y
+
+
+@pytest.mark.parametrize('n,p', [(60, 3), (128, 2), (300, 5), (1024, 8)])
+def test_lml_batched_matches_sklearn(n, p):
+    import torch
+    from batman_b200 import kernel_spec
+    from batman_b200.fit import normalise_y
+    from batman_b200.lml import lml_batched
+    X, y = _data(n, p)
+    yn, _, _ = normalise_y(y)
+    kern = ConstantKernel(1.0) * Matern(length_scale=[1.0] * p, nu=1.5)
+    gp = GaussianProcessRegressor(kernel=kern, normalize_y=True, optimizer=None).fit(X, y)
+    rng = np.random.RandomState(1)
+    thetas = [kern.theta] + [kern.theta + rng.uniform(-1.5, 1.5, size=p + 1) for _ in range(6)]
+    want = np.array([gp.log_marginal_likelihood(t) for t in thetas])
+    specs = [kernel_spec.flatten(kern.clone_with_theta(t), p) for t in thetas]
+    got = lml_batched(torch.from_numpy(X).cuda(), torch.from_numpy(yn).cuda(), specs)
+    np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-7)
+    # oracle restatement agrees too
+    mine = np.array([ogp.lml(ogp.from_sklearn(kern.clone_with_theta(t)), X, yn) for t in thetas])
+    np.testing.assert_allclose(got, mine, rtol=1e-9, atol=1e-7)
+
+
+def test_lml_other_kernels_and_noise():
+    import torch
+    from batman_b200 import kernel_spec
+    from batman_b200.fit import normalise_y
+    from batman_b200.lml import lml_batched
+    X, y = _data(200, 4)
+    yn, _, _ = normalise_y(y)
+    Xd, yd = torch.from_numpy(X).cuda(), torch.from_numpy(yn).cuda()
+    for kern in [ConstantKernel(2.0) * RBF(length_scale=[0.5, 1.0, 1.5, 2.0]) + WhiteKernel(1e-3),
+                 Matern(length_scale=0.8, nu=2.5) + WhiteKernel(0.5),
+                 ConstantKernel(0.7) + Matern(length_scale=0.5, nu=0.5) + WhiteKernel(1.0)]:
+        gp = GaussianProcessRegressor(kernel=kern, normalize_y=True, optimizer=None).fit(X, y)
+        got = lml_batched(Xd, yd, [kernel_spec.flatten(kern, 4)])
+        assert got[0] == pytest.approx(gp.log_marginal_likelihood(kern.theta), rel=1e-9, abs=1e-7)
+
+
+def test_lml_not_positive_definite_is_minus_inf():
+    """sklearn:_gpr.py:591-593: a failed Cholesky gives -inf, and must not poison its batch neighbours."""
+    import torch
+    from batman_b200 import kernel_spec
+    from batman_b200.fit import normalise_y
+    from batman_b200.lml import lml_batched
+    X, y = _data(150, 3)
+    yn, _, _ = normalise_y(y)
+    good = kernel_spec.flatten(ConstantKernel(1.0) * Matern(length_scale=[1.0] * 3, nu=1.5), 3)
+    bad = kernel_spec.KernelSpec(good.kind, 0.0, -1.0, 1.0, good.ls)       # negative definite off-diagonal mass
+    bad2 = kernel_spec.KernelSpec(good.kind, 5.0, 1.0, 1.0, good.ls)       # kdiag << row sums: indefinite
+    got = lml_batched(torch.from_numpy(X).cuda(), torch.from_numpy(yn).cuda(), [good, bad, good, bad2])
+    assert np.isfinite(got[0]) and got[0] == got[2]
+    assert got[1] == -np.inf and got[3] == -np.inf
+
+
+@pytest.mark.parametrize('n,p', [(100, 3), (517, 6)])
+def test_factorise_matches_sklearn_state(n, p):
+    import torch
+    from scipy.linalg import cholesky
+    from batman_b200 import Kriging
+    X, y = _data(n, p)
+    kern = ConstantKernel(1.7, constant_value_bounds='fixed') * Matern(
+        length_scale=list(np.linspace(0.6, 1.8, p)), length_scale_bounds='fixed', nu=1.5)
+    k = Kriging(X, y[:, None], kernel=kern)             # no free hyper-parameter: factorisation only
+    ref = GaussianProcessRegressor(kernel=kern, normalize_y=True, optimizer=None).fit(X, y)
+    gp = k.gp_models[0]
+    np.testing.assert_allclose(gp.L_, ref.L_, rtol=0, atol=1e-11)
+    np.testing.assert_allclose(gp.alpha_, ref.alpha_, rtol=1e-6, atol=1e-9 * np.abs(ref.alpha_).max())
+    assert gp.log_marginal_likelihood_value_ == pytest.approx(ref.log_marginal_likelihood_value_, rel=1e-10, abs=1e-8)
+    pts = np.random.RandomState(3).rand(500, p)
+    mean, sigma = k.evaluate(pts)
+    rm, rs = ref.predict(pts, return_std=True)
+    np.testing.assert_allclose(mean[:, 0], rm, rtol=0, atol=1e-8 * np.abs(rm).max())
+    np.testing.assert_allclose(sigma[:, 0] ** 2, rs ** 2, rtol=0, atol=1e-9 * ref._y_train_std ** 2 * 1.7)
+
+
+def test_global_optimizer_finds_at_least_sklearns_optimum():
+    """Default Kriging(): 3 DE runs (vectorised, one batched LML per generation) + polish."""
+    from batman_b200 import Kriging
+    np.random.seed(123456)
+    X = ofun.halton(40, 2, [[0.0, 0.0], [1.0, 1.0]])
+    y = ofun.michalewicz(np.pi * X)
+    k = Kriging(X, y)
+    ref = GaussianProcessRegressor(kernel=ConstantKernel() * Matern(length_scale=(1.0, 1.0),
+                                                                    length_scale_bounds=[(0.01, 100)] * 2),
+                                   normalize_y=True, n_restarts_optimizer=20, random_state=0).fit(X, y[:, 0])
+    assert k.gp_models[0].log_marginal_likelihood_value_ >= ref.log_marginal_likelihood_value_ - 1e-3
+    assert k.hyperparameter[0].shape == (3,)
+    # LML at the theta we report must be what sklearn computes at that theta
+    assert k.gp_models[0].log_marginal_likelihood_value_ == pytest.approx(
+        ref.log_marginal_likelihood(k.gp_models[0].kernel_.theta), rel=1e-8, abs=1e-7)

@@ -20,6 +20,7 @@ SIGNATURES = {
     'bk_device_info': (ctypes.c_int, [c_int_p, c_int_p, c_int_p]),
     'bk_profile_enable': (ctypes.c_int, [ctypes.c_int]),
     'bk_profile_read': (ctypes.c_int, [c_double_p, ctypes.POINTER(ctypes.c_long)]),
+    'bk_debug_fastmath': (ctypes.c_int, [vp, ctypes.c_long, vp, vp, vp]),
     'bk_gp_create': (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     'bk_gp_destroy': (ctypes.c_int, [vp]),
     'bk_gp_padded_dim': (ctypes.c_int, [ctypes.c_int]),

@@ -52,6 +52,7 @@ int launch_sobol_y(const double* y, long ld_block, long count, int p, int F, int
 int launch_reduce_slots(const double* partials, int F, int nsums, double* totals, cudaStream_t st);
 int launch_finalize(const double* totals, long N, int p, int F, int second, double* out, cudaStream_t st);
 size_t sobol_result_len(int p, int F);
+int launch_debug_fastmath(const double* in, long n, double* o_sqrt, double* o_exp, cudaStream_t st);
 size_t lml_workspace_bytes(int n, int R, bool with_wt);
 int lml_batched(const double* X, const double* y, int n, int p, int R, const int* kinds, const double* c0,
                 const double* c1, const double* kdiag, const double* ls, double* lml_out, void* ws, size_t ws_bytes,
@@ -104,6 +105,11 @@ int bk_profile_read(double* ms_by_cat, long* launches_by_cat) {
     }
     g_prof_events.clear();
     return 0;
+}
+
+int bk_debug_fastmath(const double* in_dev, long n, double* sqrt_dev, double* exp_neg_dev, void* stream) {
+    if (!in_dev || !sqrt_dev || !exp_neg_dev) return set_error("bk_debug_fastmath: NULL pointer");
+    return launch_debug_fastmath(in_dev, n, sqrt_dev, exp_neg_dev, (cudaStream_t)stream);
 }
 
 int bk_gp_padded_dim(int p) { return padded_dim(p); }

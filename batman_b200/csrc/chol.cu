@@ -495,7 +495,7 @@ int gp_factorise(const double* X, const double* y, int n, int p, int kind, doubl
     BK_LAUNCH_CHECK("k_alpha_from_wt");
     BK_CUDA(cudaMemcpyAsync(L_out, w.M, sizeof(double) * n_pad * n_pad, cudaMemcpyDeviceToDevice, st));
     if (wt_tiles_out)
-        if (int rc = launch_pack_w_ex(WT, n_pad, n_pad, 1, wt_tiles_out, st)) return rc;
+        if (int rc = launch_pack_w_ex(WT, n, n_pad, 1, wt_tiles_out, st)) return rc;   // padded rows/cols -> 0
     return 0;
 }
 
@@ -523,7 +523,7 @@ int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, void* ws, siz
         BK_LAUNCH_CHECK("k_diag_block<false>");
     }
     if (int rc = trtri_sweep(w.M, w.Winv, WT, n, st)) return rc;
-    return launch_pack_w_ex(WT, n_pad, n_pad, 1, wt_tiles_out, st);
+    return launch_pack_w_ex(WT, n, n_pad, 1, wt_tiles_out, st);   // padded rows/cols -> 0
 }
 
 }  // namespace bk

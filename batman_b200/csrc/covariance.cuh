@@ -5,6 +5,7 @@
 // in scipy cdist order (sequential, non-fused s += d*d).
 #pragma once
 #include "../../include/batman_b200.h"
+#include "fastmath.cuh"
 
 namespace bk {
 
@@ -14,19 +15,19 @@ constexpr double SQRT5 = 2.23606797749979;     // math.sqrt(5)
 template <int KIND>
 __device__ __forceinline__ double stationary(double s) {
     if constexpr (KIND == BK_MATERN12) {
-        return exp(-sqrt(s));                                       // np.exp(-dists)
+        return bk_exp_neg(-bk_sqrt(s));                                       // np.exp(-dists)
     } else if constexpr (KIND == BK_MATERN32) {
-        double t = __dmul_rn(sqrt(s), SQRT3);                       // K = dists * math.sqrt(3)
-        return __dmul_rn(__dadd_rn(1.0, t), exp(-t));               // (1.0 + K) * np.exp(-K)
+        double t = __dmul_rn(bk_sqrt(s), SQRT3);                       // K = dists * math.sqrt(3)
+        return __dmul_rn(__dadd_rn(1.0, t), bk_exp_neg(-t));        // (1.0 + K) * np.exp(-K)
     } else if constexpr (KIND == BK_MATERN52) {
-        double t = __dmul_rn(sqrt(s), SQRT5);                       // K = dists * math.sqrt(5)
+        double t = __dmul_rn(bk_sqrt(s), SQRT5);                       // K = dists * math.sqrt(5)
         double q = __ddiv_rn(__dmul_rn(t, t), 3.0);                 // K**2 / 3.0
-        return __dmul_rn(__dadd_rn(__dadd_rn(1.0, t), q), exp(-t)); // (1.0 + K + K**2/3.0) * np.exp(-K)
+        return __dmul_rn(__dadd_rn(__dadd_rn(1.0, t), q), bk_exp_neg(-t)); // (1.0 + K + K**2/3.0) * np.exp(-K)
     } else if constexpr (KIND == BK_RBF) {
-        return exp(__dmul_rn(-0.5, s));                             // np.exp(-0.5 * sqeuclidean)
+        return bk_exp_neg(__dmul_rn(-0.5, s));                      // np.exp(-0.5 * sqeuclidean)
     } else {
-        double d = sqrt(s);
-        return exp(-__dmul_rn(__dmul_rn(d, d), 0.5));               // np.exp(-(dists**2) / 2.0)
+        double d = bk_sqrt(s);
+        return bk_exp_neg(-__dmul_rn(__dmul_rn(d, d), 0.5));               // np.exp(-(dists**2) / 2.0)
     }
 }
 

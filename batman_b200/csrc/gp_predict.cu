@@ -209,6 +209,21 @@ static int launch_predict_k(const bk_gp_s* h, int q, const double* pts, long k, 
     return set_error("unsupported padded dimension %d", h->P);
 }
 
+__global__ void k_debug_fastmath(const double* __restrict__ in, long n, double* __restrict__ o_sqrt,
+                                 double* __restrict__ o_exp) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = in[i];
+    o_sqrt[i] = bk_sqrt(v);
+    o_exp[i] = bk_exp_neg(-v);
+}
+int launch_debug_fastmath(const double* in, long n, double* o_sqrt, double* o_exp, cudaStream_t st) {
+    if (n <= 0) return 0;
+    k_debug_fastmath<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, n, o_sqrt, o_exp);
+    BK_LAUNCH_CHECK("k_debug_fastmath");
+    return 0;
+}
+
 // mean of output q at k points; if kstar != null also the packed K* tiles for gp_var
 int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar, cudaStream_t st) {
     switch (h->out[q].kind) {

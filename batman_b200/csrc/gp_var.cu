@@ -14,7 +14,8 @@
 // panel it runs a 128x128 output tile over k = 0..(panel+1)*128 with
 // mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4): 8 warps as 2(M) x 4(N), warp tile
 // 64x32 = 32 accumulator fragments.  Operands are staged by cp.async.bulk
-// (UBLKCP) through a 4-stage mbarrier ring; both W and K* live in HBM already
+// (UBLKCP) through a 6-stage full/empty mbarrier ring (no block-wide barrier in the sweep; lane 0 of warp 0
+// is the producer); both W and K* live in HBM already
 // in fragment-major order, so each 16 KiB stage is ONE contiguous bulk copy and
 // every fragment load is a conflict-free LDS.128.
 //
@@ -32,10 +33,30 @@
 
 namespace bk {
 
-constexpr int VAR_THREADS = 256;
-constexpr int VAR_STAGES = 4;
+constexpr int VAR_CONSUMERS = 8;                       // DMMA warps (2 per SM sub-partition: 16 K registers each)
+constexpr int VAR_THREADS = VAR_CONSUMERS * 32;        // lane 0 of warp 0 doubles as the TMA producer
+constexpr int VAR_STAGES = 6;
+constexpr int VAR_LAG = 2;                             // a stage is refilled 2 steps after warp 0 left it
 constexpr size_t VAR_STAGE_BYTES = 2 * TILE_DOUBLES * 8;   // A + B
-constexpr size_t VAR_SMEM = VAR_STAGES * VAR_STAGE_BYTES + 2 * TILE_T * 8 + VAR_STAGES * 8;
+constexpr size_t VAR_SMEM = VAR_STAGES * VAR_STAGE_BYTES + 2 * TILE_T * 8 + 2 * VAR_STAGES * 8;
+
+// one k8 step (two DMMA k4 steps) of a warp tile, m-tiles MT_LO..7 only
+template <int MT_LO>
+__device__ __forceinline__ void var_k8_step(double (&c)[8][4][2], const double2* __restrict__ As,
+                                            const double2* __restrict__ Bs, int wm, int wn, int k8, int lane) {
+    double2 a[8], b[4];
+#pragma unroll
+    for (int mt = MT_LO; mt < 8; ++mt) a[mt] = As[(((mt * 2 + wm) * 2 + k8) * 32) + lane];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[(((wn * 4 + nt) * 2 + k8) * 32) + lane];
+#pragma unroll
+    for (int mt = MT_LO; mt < 8; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            dmma884(c[mt][nt][0], c[mt][nt][1], a[mt].x, b[nt].x);
+            dmma884(c[mt][nt][0], c[mt][nt][1], a[mt].y, b[nt].y);
+        }
+}
 
 __global__ void __launch_bounds__(VAR_THREADS, 1)
 k_var_trmm(const double* __restrict__ wt, const double* __restrict__ kstar, int n_pad, double kdiag, double y_std,
@@ -43,7 +64,8 @@ k_var_trmm(const double* __restrict__ wt, const double* __restrict__ kstar, int 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* stage = reinterpret_cast<double*>(smem_raw);
     double* red = stage + VAR_STAGES * 2 * TILE_DOUBLES;                 // [2][128]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(red + 2 * TILE_T);
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * TILE_T);      // [STAGES] TMA -> consumers
+    uint64_t* empty = full + VAR_STAGES;                                 // [STAGES] consumers -> TMA
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp >> 2, wn = warp & 3;
@@ -53,78 +75,90 @@ k_var_trmm(const double* __restrict__ wt, const double* __restrict__ kstar, int 
     const double* kt = kstar + (size_t)blockIdx.x * njb * TILE_DOUBLES;
 
     if (tid == 0) {
-        for (int s = 0; s < VAR_STAGES; ++s) mbar_init(&bar[s], 1);
+        for (int s = 0; s < VAR_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], VAR_CONSUMERS);
+        }
         mbar_fence_init();
     }
     __syncthreads();
-
-    // producer cursor (thread 0 only)
-    int p_step = 0, p_panel = 0, p_jb = 0;
-    auto produce = [&]() {
-        const int s = p_step % VAR_STAGES;
-        double* dst = stage + (size_t)s * 2 * TILE_DOUBLES;
-        mbar_expect_tx(&bar[s], (uint32_t)VAR_STAGE_BYTES);
-        tma_load_1d(dst, wt + ((size_t)p_panel * njb + p_jb) * TILE_DOUBLES, TILE_DOUBLES * 8, &bar[s]);
-        tma_load_1d(dst + TILE_DOUBLES, kt + (size_t)p_jb * TILE_DOUBLES, TILE_DOUBLES * 8, &bar[s]);
-        ++p_step;
-        if (++p_jb == (p_panel + 1) * (TILE_M / TILE_K)) { p_jb = 0; ++p_panel; }
-    };
-    if (tid == 0)
-        for (int s = 0; s < VAR_STAGES && p_step < total_steps; ++s) produce();
 
     double colsum[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) colsum[nt][0] = colsum[nt][1] = 0.0;
 
-    int step = 0;
-    for (int panel = 0; panel < n_panels; ++panel) {
-        double c[8][4][2];
-#pragma unroll
-        for (int mt = 0; mt < 8; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) c[mt][nt][0] = c[mt][nt][1] = 0.0;
+    // producer cursor (lane 0 of warp 0): streams (W tile, K* tile) pairs through the ring
+    int p_step = 0, p_panel = 0, p_jb = 0;
+    auto produce = [&]() {
+        const int s = p_step % VAR_STAGES;
+        if (p_step >= VAR_STAGES) mbar_wait(&empty[s], ((p_step / VAR_STAGES) - 1) & 1);
+        double* dst = stage + (size_t)s * 2 * TILE_DOUBLES;
+        mbar_expect_tx(&full[s], (uint32_t)VAR_STAGE_BYTES);
+        tma_load_1d(dst, wt + ((size_t)p_panel * njb + p_jb) * TILE_DOUBLES, TILE_DOUBLES * 8, &full[s]);
+        tma_load_1d(dst + TILE_DOUBLES, kt + (size_t)p_jb * TILE_DOUBLES, TILE_DOUBLES * 8, &full[s]);
+        ++p_step;
+        if (++p_jb == (p_panel + 1) * (TILE_M / TILE_K)) { p_jb = 0; ++p_panel; }
+    };
+    if (tid == 0)
+        for (int s = 0; s < VAR_STAGES - VAR_LAG && p_step < total_steps; ++s) produce();
 
-        const int nsteps = (panel + 1) * (TILE_M / TILE_K);
-        for (int jb = 0; jb < nsteps; ++jb, ++step) {
-            const int s = step % VAR_STAGES;
-            mbar_wait(&bar[s], (step / VAR_STAGES) & 1);
-            const double2* As = reinterpret_cast<const double2*>(stage + (size_t)s * 2 * TILE_DOUBLES);
-            const double2* Bs = As + TILE_DOUBLES / 2;
-            // Diagonal block of the panel: W is lower triangular, so the 8x8 sub-block (m-tile, k8-step) is
-            // identically zero when its rows lie above its columns.  M-tiles are dealt to the two warp rows
-            // round-robin (m-tile = 2*mt + wm) so both carry the same share of the surviving sub-blocks.
-            const int kk8_base = (jb - panel * (TILE_M / TILE_K)) * 2;   // >= 0 only inside the diagonal block
+    {
+        // ===== no block-wide barrier inside the sweep: each warp frees its stage itself (empty[s]) and the
+        // producer lane refills a stage VAR_LAG steps after its own warp left it, so it practically never waits =====
+        int step = 0;
+        for (int panel = 0; panel < n_panels; ++panel) {
+            double c[8][4][2];
 #pragma unroll
-            for (int k8 = 0; k8 < 2; ++k8) {
-                const int kk8 = kk8_base + k8;
-                const int mt_lo = kk8 > wm ? (kk8 - wm + 1) >> 1 : 0;    // first mt with 2*mt + wm >= kk8
-                double2 a[8], b[4];
+            for (int mt = 0; mt < 8; ++mt)
 #pragma unroll
-                for (int mt = 0; mt < 8; ++mt)
-                    if (mt >= mt_lo) a[mt] = As[(((mt * 2 + wm) * 2 + k8) * 32) + lane];
+                for (int nt = 0; nt < 4; ++nt) c[mt][nt][0] = c[mt][nt][1] = 0.0;
+
+            const int nsteps = (panel + 1) * (TILE_M / TILE_K);
+            for (int jb = 0; jb < nsteps; ++jb, ++step) {
+                const int s = step % VAR_STAGES;
+                if (tid == 0 && p_step < total_steps) produce();
+                __syncwarp();
+                mbar_wait(&full[s], (step / VAR_STAGES) & 1);
+                const double2* As = reinterpret_cast<const double2*>(stage + (size_t)s * 2 * TILE_DOUBLES);
+                const double2* Bs = As + TILE_DOUBLES / 2;
+                // Diagonal block of the panel: W is lower triangular, so the 8x8 sub-block (m-tile, k8-step) is
+                // identically zero when its rows lie above its columns.  M-tiles are dealt to the two warp rows
+                // round-robin (m-tile = 2*mt + wm) so both carry the same share of the surviving sub-blocks.  The
+                // skip is a warp-uniform BRANCH to a shorter unrolled body (a predicated-off DMMA still costs).
+                const int kk8_base = (jb - panel * (TILE_M / TILE_K)) * 2;   // >= 0 only inside the diagonal block
+                if (kk8_base + 1 <= wm) {
+                    var_k8_step<0>(c, As, Bs, wm, wn, 0, lane);
+                    var_k8_step<0>(c, As, Bs, wm, wn, 1, lane);
+                } else {
 #pragma unroll
-                for (int nt = 0; nt < 4; ++nt) b[nt] = Bs[(((wn * 4 + nt) * 2 + k8) * 32) + lane];
-#pragma unroll
-                for (int mt = 0; mt < 8; ++mt)
-                    if (mt >= mt_lo) {
-#pragma unroll
-                        for (int nt = 0; nt < 4; ++nt) {
-                            dmma884(c[mt][nt][0], c[mt][nt][1], a[mt].x, b[nt].x);
-                            dmma884(c[mt][nt][0], c[mt][nt][1], a[mt].y, b[nt].y);
+                    for (int k8 = 0; k8 < 2; ++k8) {
+                        const int kk8 = kk8_base + k8;
+                        const int mt_lo = kk8 > wm ? (kk8 - wm + 1) >> 1 : 0;    // first mt with 2*mt + wm >= kk8
+                        switch (mt_lo) {
+                            case 0: var_k8_step<0>(c, As, Bs, wm, wn, k8, lane); break;
+                            case 1: var_k8_step<1>(c, As, Bs, wm, wn, k8, lane); break;
+                            case 2: var_k8_step<2>(c, As, Bs, wm, wn, k8, lane); break;
+                            case 3: var_k8_step<3>(c, As, Bs, wm, wn, k8, lane); break;
+                            case 4: var_k8_step<4>(c, As, Bs, wm, wn, k8, lane); break;
+                            case 5: var_k8_step<5>(c, As, Bs, wm, wn, k8, lane); break;
+                            case 6: var_k8_step<6>(c, As, Bs, wm, wn, k8, lane); break;
+                            case 7: var_k8_step<7>(c, As, Bs, wm, wn, k8, lane); break;
+                            default: break;
                         }
                     }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);   // this warp's fragment loads of stage s are done
             }
-            __syncthreads();   // stage s fully consumed
-            if (tid == 0 && p_step < total_steps) produce();
+            // fold this row panel into the running column sums of squares
+#pragma unroll
+            for (int mt = 0; mt < 8; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    colsum[nt][0] = fma(c[mt][nt][0], c[mt][nt][0], colsum[nt][0]);
+                    colsum[nt][1] = fma(c[mt][nt][1], c[mt][nt][1], colsum[nt][1]);
+                }
         }
-        // fold this row panel into the running column sums of squares
-#pragma unroll
-        for (int mt = 0; mt < 8; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                colsum[nt][0] = fma(c[mt][nt][0], c[mt][nt][0], colsum[nt][0]);
-                colsum[nt][1] = fma(c[mt][nt][1], c[mt][nt][1], colsum[nt][1]);
-            }
     }
 
     // reduce over the 8 row groups of the fragment (lanes differing in g = lane/4), then over wm

@@ -111,6 +111,7 @@ class DeviceModel:
 
     def predict_device(self, pts_dev, return_std=True):
         """pts_dev: (k, p) float64 CUDA tensor -> (mean, std) CUDA tensors (k, m); std None if not requested."""
+        pts_dev = pts_dev.contiguous()          # the C ABI takes dense row-major buffers
         k = pts_dev.shape[0]
         mean = torch.empty((k, self.m), dtype=torch.float64, device=self.device)
         std = torch.empty((k, self.m), dtype=torch.float64, device=self.device) if return_std else None

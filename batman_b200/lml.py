@@ -38,6 +38,7 @@ def _workspace(device, nbytes):
 def lml_batched(X_dev, y_dev, specs):
     """X_dev (n, p), y_dev (n,) CUDA float64 tensors; specs: list of KernelSpec -> numpy (R,) LML values."""
     lib = _lib.load()
+    X_dev, y_dev = X_dev.contiguous(), y_dev.contiguous()     # the C ABI takes dense row-major buffers
     n, p = X_dev.shape
     R = len(specs)
     out = np.empty(R)
@@ -65,6 +66,7 @@ def factorise(X_dev, y_dev, spec):
 
     -> (L (n, n) numpy lower, alpha (n,) numpy, lml float, packed L^-1 tiles as a CUDA tensor)."""
     lib = _lib.load()
+    X_dev, y_dev = X_dev.contiguous(), y_dev.contiguous()
     n, p = X_dev.shape
     n_pad = lib.bk_gp_padded_n(n)
     dev = X_dev.device

@@ -50,6 +50,9 @@ int bk_device_info(int* sm_count, int* cc_major, int* cc_minor);
 int bk_profile_enable(int on);
 int bk_profile_read(double* ms_by_cat, long* launches_by_cat);
 
+/* Diagnostics: the kernels' own branch-free sqrt(v) and exp(-v) (csrc/fastmath.cuh) on n values v >= 0. */
+int bk_debug_fastmath(const double* in_dev, long n, double* sqrt_dev, double* exp_neg_dev, void* stream);
+
 /* ---- model state: replaces the fitted attributes of the m GaussianProcessRegressor
  *      objects held in Kriging.gp_models (kriging.py:148; sklearn:_gpr.py:349-367) ---- */
 int bk_gp_create(bk_gp_t* out, int n_train, int p, int m);

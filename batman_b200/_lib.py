@@ -45,6 +45,11 @@ SIGNATURES = {
                                       c_double_p, ctypes.c_int, vp, vp]),
     'bk_sobol_accumulate': (ctypes.c_int, [vp, vp, vp, ctypes.c_uint64, c_int_p, c_double_p, ctypes.c_long,
                                            ctypes.c_long, ctypes.c_int, c_double_p, vp, vp]),
+    'bk_sobol_modes': (ctypes.c_int, [vp, vp, vp, ctypes.c_uint64, c_int_p, c_double_p, ctypes.c_long, ctypes.c_long,
+                                      ctypes.c_int, vp, vp]),
+    'bk_pod_inverse': (ctypes.c_int, [vp, ctypes.c_long, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp]),
+    'bk_pod_sobol_accumulate': (ctypes.c_int, [vp, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp,
+                                               ctypes.c_int, vp, vp, vp]),
     'bk_sobol_accumulate_y': (ctypes.c_int, [vp, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, vp, vp, vp]),
     'bk_sobol_reduce_slots': (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp]),

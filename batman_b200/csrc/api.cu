@@ -44,7 +44,11 @@ int launch_var(const bk_gp_s* h, int q, const double* kstar, long k, double* std
 int launch_pack_w(const double* w, int n, double* out, cudaStream_t st);
 int launch_sobol(const bk_gp_s* h, int q, const double* a, const double* b, uint64_t seed, const int* mkind,
                  const double* mpar, long row_lo, long count, int second, double shift, double* partials,
-                 cudaStream_t st);
+                 double* yout, cudaStream_t st);
+int launch_pod_inverse(const double* modes, long k, int m, const double* U, const double* mean, int F, double* out,
+                       cudaStream_t st);
+int launch_pod_sobol(const double* ymodes, long count, int p, int m, int second, const double* U, const double* mean,
+                     int F, const double* shift, double* partials, cudaStream_t st);
 int launch_design_rows(uint64_t seed, long row_lo, long count, int p, const int* mkind, const double* mpar,
                        int stream_id, double* out, cudaStream_t st);
 int launch_sobol_y(const double* y, long ld_block, long count, int p, int F, int second, const double* shift,
@@ -255,10 +259,42 @@ int bk_sobol_accumulate(bk_gp_t h, const double* a_dev, const double* b_dev, uin
     if (count <= 0) return 0;
     for (int q = 0; q < h->m; ++q)
         if (int rc = launch_sobol(h, q, a_dev, b_dev, seed, marg_kind_host, marg_par_host, row_lo, count,
-                                  second_order ? 1 : 0, shift_host ? shift_host[q] : 0.0, partials_dev,
+                                  second_order ? 1 : 0, shift_host ? shift_host[q] : 0.0, partials_dev, nullptr,
                                   (cudaStream_t)stream))
             return rc;
     return 0;
+}
+
+int bk_sobol_modes(bk_gp_t h, const double* a_dev, const double* b_dev, uint64_t seed, const int* marg_kind_host,
+                   const double* marg_par_host, long row_lo, long count, int second_order, double* ymodes_dev,
+                   void* stream) {
+    if (!h || !ymodes_dev) return set_error("bk_sobol_modes: NULL pointer");
+    if ((a_dev == nullptr) != (b_dev == nullptr)) return set_error("bk_sobol_modes: a_dev and b_dev must both be given or both NULL");
+    if (!a_dev && (!marg_kind_host || !marg_par_host))
+        return set_error("bk_sobol_modes: no base samples and no marginals to generate them from");
+    if (count <= 0) return 0;
+    for (int q = 0; q < h->m; ++q)
+        if (int rc = launch_sobol(h, q, a_dev, b_dev, seed, marg_kind_host, marg_par_host, row_lo, count,
+                                  second_order ? 1 : 0, 0.0, nullptr, ymodes_dev, (cudaStream_t)stream))
+            return rc;
+    return 0;
+}
+
+int bk_pod_inverse(const double* modes_dev, long k, int m, const double* u_dev, const double* mean_dev, int F,
+                   double* out_dev, void* stream) {
+    if (!modes_dev || !u_dev || !mean_dev || !out_dev) return set_error("bk_pod_inverse: NULL pointer");
+    if (m < 1 || F < 1) return set_error("bk_pod_inverse: m and F must be >= 1");
+    return launch_pod_inverse(modes_dev, k, m, u_dev, mean_dev, F, out_dev, (cudaStream_t)stream);
+}
+
+int bk_pod_sobol_accumulate(const double* ymodes_dev, long count, int p, int m, int second_order,
+                            const double* u_dev, const double* mean_dev, int F, const double* shift_dev,
+                            double* partials_dev, void* stream) {
+    if (!ymodes_dev || !u_dev || !mean_dev || !shift_dev || !partials_dev)
+        return set_error("bk_pod_sobol_accumulate: NULL pointer");
+    if (p < 1 || m < 1 || F < 1) return set_error("bk_pod_sobol_accumulate: p, m, F must be >= 1");
+    return launch_pod_sobol(ymodes_dev, count, p, m, second_order ? 1 : 0, u_dev, mean_dev, F, shift_dev,
+                            partials_dev, (cudaStream_t)stream);
 }
 
 int bk_sobol_accumulate_y(const double* y_dev, long ld_block, long count, int p, int F, int second_order,

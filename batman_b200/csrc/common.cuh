@@ -14,7 +14,7 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // ---------------------------------------------------------------- optional per-kernel CUDA-event timing
 // (bk_profile_enable / bk_profile_read in the C ABI; used by bench.py for the roofline numbers)
-enum ProfCat { PROF_PREDICT = 0, PROF_VAR = 1, PROF_SOBOL = 2, PROF_SOBOL_Y = 3, PROF_OTHER = 4, PROF_CHOL = 5, PROF_NCAT = 8 };
+enum ProfCat { PROF_PREDICT = 0, PROF_VAR = 1, PROF_SOBOL = 2, PROF_SOBOL_Y = 3, PROF_OTHER = 4, PROF_CHOL = 5, PROF_POD = 6, PROF_NCAT = 8 };
 struct ProfScope {
     cudaStream_t st;
     int idx;

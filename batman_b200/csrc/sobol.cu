@@ -165,6 +165,8 @@ struct SobolParams {
     double c0, c1, y_mean, y_std, shift;
     double* partial;       // slot 0 of this output; slots are slot_stride doubles apart
     long slot_stride;
+    double* yout;          // if set: write the (unshifted) outputs [nb][count][m] instead of reducing them
+    int m, q;
 };
 
 template <int KIND, int P>
@@ -281,21 +283,27 @@ __global__ void __launch_bounds__(SOB_THREADS) k_sobol(const SobolParams<P> prm)
             for (int bb = 0; bb < SOB_CH; ++bb) {
                 if (b0 + bb < prm.nb) {
                     const double y = __dadd_rn(__dmul_rn(prm.y_std, acc[bb]), prm.y_mean);
-                    y_s[(b0 + bb) * SOB_THREADS + tid] = valid ? __dadd_rn(y, -prm.shift) : 0.0;
+                    if (prm.yout) {
+                        if (valid) prm.yout[((size_t)(b0 + bb) * prm.count + g) * prm.m + prm.q] = y;
+                    } else {
+                        y_s[(b0 + bb) * SOB_THREADS + tid] = valid ? __dadd_rn(y, -prm.shift) : 0.0;
+                    }
                 }
             }
         }
-        saltelli_products([&](int b) { return y_s[b * SOB_THREADS + tid]; }, prm.p, prm.second, lane,
-                          wsum + (size_t)warp * prm.nsums * 2);
+        if (!prm.yout)
+            saltelli_products([&](int b) { return y_s[b * SOB_THREADS + tid]; }, prm.p, prm.second, lane,
+                              wsum + (size_t)warp * prm.nsums * 2);
     }
     __syncthreads();
-    flush_slot(wsum, SOB_THREADS / 32, prm.nsums, prm.partial + (size_t)blockIdx.x * prm.slot_stride);
+    if (!prm.yout)
+        flush_slot(wsum, SOB_THREADS / 32, prm.nsums, prm.partial + (size_t)blockIdx.x * prm.slot_stride);
 }
 
 template <int KIND, int P>
 static int launch_sobol_kp(const bk_gp_s* h, int q, const double* a, const double* b, uint64_t seed,
                            const int* mkind, const double* mpar, long row_lo, long count, int second,
-                           double shift, double* partials, cudaStream_t st) {
+                           double shift, double* partials, double* yout, cudaStream_t st) {
     const GpOutput& o = h->out[q];
     SobolParams<P> prm;
     prm.a = a; prm.b = b; prm.seed = seed;
@@ -312,7 +320,8 @@ static int launch_sobol_kp(const bk_gp_s* h, int q, const double* a, const doubl
     prm.n_pad = h->n_pad; prm.xs = o.xs; prm.alpha = o.alpha;
     prm.c0 = o.c0; prm.c1 = o.c1; prm.y_mean = o.y_mean; prm.y_std = o.y_std; prm.shift = shift;
     prm.slot_stride = (long)h->m * prm.nsums * 2;
-    prm.partial = partials + (size_t)q * prm.nsums * 2;
+    prm.partial = partials ? partials + (size_t)q * prm.nsums * 2 : nullptr;
+    prm.yout = yout; prm.m = h->m; prm.q = q;
     const size_t smem = ((size_t)2 * SOB_TJ * P + 2 * SOB_TJ + (size_t)prm.nb * SOB_THREADS + 4 * prm.nsums * 2) * 8 + 16;
     BK_CUDA(cudaFuncSetAttribute(k_sobol<KIND, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope prof(PROF_SOBOL, st);
@@ -324,8 +333,8 @@ static int launch_sobol_kp(const bk_gp_s* h, int q, const double* a, const doubl
 template <int KIND>
 static int launch_sobol_k(const bk_gp_s* h, int q, const double* a, const double* b, uint64_t seed, const int* mkind,
                           const double* mpar, long row_lo, long count, int second, double shift, double* partials,
-                          cudaStream_t st) {
-#define BK_CASE(PP) case PP: return launch_sobol_kp<KIND, PP>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, st);
+                          double* yout, cudaStream_t st) {
+#define BK_CASE(PP) case PP: return launch_sobol_kp<KIND, PP>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, yout, st);
     switch (h->P) {
         BK_CASE(2) BK_CASE(4) BK_CASE(6) BK_CASE(8) BK_CASE(10) BK_CASE(12) BK_CASE(16) BK_CASE(20) BK_CASE(24) BK_CASE(32)
     }
@@ -335,13 +344,13 @@ static int launch_sobol_k(const bk_gp_s* h, int q, const double* a, const double
 
 int launch_sobol(const bk_gp_s* h, int q, const double* a, const double* b, uint64_t seed, const int* mkind,
                  const double* mpar, long row_lo, long count, int second, double shift, double* partials,
-                 cudaStream_t st) {
+                 double* yout, cudaStream_t st) {
     switch (h->out[q].kind) {
-        case BK_MATERN12: return launch_sobol_k<BK_MATERN12>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, st);
-        case BK_MATERN32: return launch_sobol_k<BK_MATERN32>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, st);
-        case BK_MATERN52: return launch_sobol_k<BK_MATERN52>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, st);
-        case BK_RBF: return launch_sobol_k<BK_RBF>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, st);
-        case BK_MATERN_INF: return launch_sobol_k<BK_MATERN_INF>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, st);
+        case BK_MATERN12: return launch_sobol_k<BK_MATERN12>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, yout, st);
+        case BK_MATERN32: return launch_sobol_k<BK_MATERN32>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, yout, st);
+        case BK_MATERN52: return launch_sobol_k<BK_MATERN52>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, yout, st);
+        case BK_RBF: return launch_sobol_k<BK_RBF>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, yout, st);
+        case BK_MATERN_INF: return launch_sobol_k<BK_MATERN_INF>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, yout, st);
     }
     return set_error("output %d has no kernel set", q);
 }

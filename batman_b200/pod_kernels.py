@@ -1,12 +1,24 @@
 """POD mode -> field step (pod/pod.py:226-228): pred = mean_snapshot + (U @ modes.T).T
 
-(k, m) x (m, F) with m <= ~20 modes and F ~ 400 features: a genuine GEMM.
-Round-1 state: dispatched to the library FP64 GEMM (torch.addmm -> cuBLAS
-DGEMM, which runs on the same DMMA pipe); the hand-written DMMA kernel that
-fuses this step with the per-feature Saltelli sums is K4 in DESIGN.md.
+Hand-written DMMA kernel (csrc/pod.cu, ``bk_pod_inverse``); the variant fused with the
+per-feature Saltelli sums is ``bk_pod_sobol_accumulate`` (used by ``UQ.sobol``).
 """
+import ctypes
+
 import torch
+
+from . import _lib
 
 
 def pod_inverse(mean_dev, U_dev, modes_dev):
-    return torch.addmm(mean_dev[None, :].expand(modes_dev.shape[0], -1), modes_dev, U_dev.t())
+    """mean (F,), U (F, m), modes (k, m) CUDA float64 tensors -> (k, F)."""
+    lib = _lib.load()
+    modes_dev = modes_dev.contiguous()
+    k, m = modes_dev.shape
+    F = U_dev.shape[0]
+    out = torch.empty((k, F), dtype=torch.float64, device=modes_dev.device)
+    with torch.cuda.device(modes_dev.device):
+        _lib.check(lib.bk_pod_inverse(ctypes.c_void_p(modes_dev.data_ptr()), k, m, ctypes.c_void_p(U_dev.data_ptr()),
+                                      ctypes.c_void_p(mean_dev.data_ptr()), F, ctypes.c_void_p(out.data_ptr()),
+                                      ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    return out

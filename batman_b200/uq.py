@@ -147,30 +147,36 @@ class UQ:
                     ptr(B_all[lo:hi]) if B_all is not None else None, self.seed, kinds, params, lo, hi - lo,
                     second, shift, ptr(partials), stream))
             else:
-                # POD field / block integral: modes are predicted chunk-wise, lifted to the field and
-                # reduced by the HBM-bound reducer (Y never exceeds one chunk)
-                ymean = torch.tensor(model.y_means, dtype=torch.float64, device=dev)[None, :]
-                shift_f = pod.inverse_transform_device(ymean)[0] if pod is not None else ymean[0]
+                # POD field / block integral: the per-block mode outputs of a chunk of base rows are stored
+                # (bk_sobol_modes), then lifted to the field on the tensor cores and reduced in one kernel
+                # (bk_pod_sobol_accumulate); the N(2p+2) x F output design never exists.
+                self.surrogate.predictor.set_input_scaler(self.surrogate.scaler.scale_, self.surrogate.scaler.min_)
+                m = model.m
+                if pod is not None:
+                    U_h, mean_h = pod.U, pod.mean_snapshot
+                else:
+                    U_h, mean_h = np.eye(m), np.zeros(m)
                 if block:
-                    shift_f = ((shift_f[1:] + shift_f[:-1]) / 2.0).sum()[None]
-                shift_f = shift_f.contiguous()
-                chunk = max(1, min(hi - lo, int((1 << 28) // max(1, nb * self.output_len))))
+                    # np.trapz(f) = sum((f[1:] + f[:-1]) / 2) is linear: integrate the basis once (uq.py:216-217)
+                    w = np.zeros(len(mean_h))
+                    if len(mean_h) > 1:
+                        w[:-1] += 0.5
+                        w[1:] += 0.5
+                    U_h, mean_h = (w @ U_h)[None, :], np.array([w @ mean_h])
+                shift_h = mean_h + U_h @ np.asarray(model.y_means)
+                U_d = torch.from_numpy(np.ascontiguousarray(U_h, dtype=np.float64)).to(dev)
+                mean_d = torch.from_numpy(np.ascontiguousarray(mean_h, dtype=np.float64)).to(dev)
+                shift_d = torch.from_numpy(np.ascontiguousarray(shift_h, dtype=np.float64)).to(dev)
+                chunk = max(1, min(hi - lo, max(1024, int((1 << 26) // max(1, nb * m)))))
+                ymodes = torch.empty(nb * chunk * m, dtype=torch.float64, device=dev)
                 for c0 in range(lo, hi, chunk):
                     cnt = min(chunk, hi - c0)
-                    if A_all is not None:
-                        A, B = A_all[c0:c0 + cnt], B_all[c0:c0 + cnt]
-                    else:
-                        A = torch.empty((cnt, p), dtype=torch.float64, device=dev)
-                        B = torch.empty((cnt, p), dtype=torch.float64, device=dev)
-                        _lib.check(lib.bk_design_rows(self.seed, c0, cnt, p, kinds, params, 0, ptr(A), stream))
-                        _lib.check(lib.bk_design_rows(self.seed, c0, cnt, p, kinds, params, 1, ptr(B), stream))
-                    D = self._design_blocks(A, B, nb)
-                    Y, _ = self.surrogate.predict_device(D.view(nb * cnt, p), return_std=False)
-                    if block:
-                        Y = ((Y[:, 1:] + Y[:, :-1]) / 2.0).sum(dim=1, keepdim=True)
-                    Y = Y.contiguous()
-                    _lib.check(lib.bk_sobol_accumulate_y(ptr(Y), cnt, cnt, p, F, second, ptr(shift_f),
-                                                         ptr(partials), stream))
+                    _lib.check(lib.bk_sobol_modes(
+                        model.handle, ptr(A_all[c0:c0 + cnt]) if A_all is not None else None,
+                        ptr(B_all[c0:c0 + cnt]) if B_all is not None else None, self.seed, kinds, params, c0, cnt,
+                        second, ptr(ymodes), stream))
+                    _lib.check(lib.bk_pod_sobol_accumulate(ptr(ymodes), cnt, p, m, second, ptr(U_d), ptr(mean_d), F,
+                                                           ptr(shift_d), ptr(partials), stream))
             self.logger.info("Created {} samples for Sobol'".format(nb * size))
         else:
             # ensemble mode (uq.py:336-339): user-supplied Saltelli output sample

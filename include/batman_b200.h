@@ -45,7 +45,7 @@ int bk_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
 /* Optional per-kernel timing with CUDA events on the launching stream (bench.py roofline numbers).
  * Categories: 0 = gp_kstar_mean (K1), 1 = gp_var_trmm (K2), 2 = fused Saltelli (K1+K3+K6),
- * 3 = Saltelli reducer over supplied outputs, 4 = everything else, 5 = LML / Cholesky / inverse (K5).  bk_profile_read synchronises,
+ * 3 = Saltelli reducer over supplied outputs, 4 = everything else, 5 = LML / Cholesky / inverse (K5), 6 = POD kernels (K4).  bk_profile_read synchronises,
  * returns the summed milliseconds and launch counts since the last read (arrays of 8) and clears. */
 int bk_profile_enable(int on);
 int bk_profile_read(double* ms_by_cat, long* launches_by_cat);
@@ -124,6 +124,21 @@ int bk_sobol_accumulate(bk_gp_t h, const double* a_dev, const double* b_dev, uin
                         const int* marg_kind_host, const double* marg_par_host, long row_lo,
                         long count, int second_order, const double* shift_host,
                         double* partials_dev, void* stream);
+/* Same design and prediction, but the per-block outputs are STORED instead of reduced:
+ * ymodes_dev[(b*count + k)*m + q] = output q of block b at base row row_lo + k  (input of bk_pod_sobol_accumulate). */
+int bk_sobol_modes(bk_gp_t h, const double* a_dev, const double* b_dev, uint64_t seed,
+                   const int* marg_kind_host, const double* marg_par_host, long row_lo, long count,
+                   int second_order, double* ymodes_dev, void* stream);
+/* Pod.inverse_transform (pod/pod.py:219-228): out_dev (k x F) = mean_dev (F) + modes_dev (k x m) . u_dev^T (F x m),
+ * FP64 tensor cores.  SurrogateModel.__call__ applies it to the mean and to sigma (surrogate_model.py:191-196). */
+int bk_pod_inverse(const double* modes_dev, long k, int m, const double* u_dev, const double* mean_dev, int F,
+                   double* out_dev, void* stream);
+/* POD field + Saltelli sums fused: lifts the stored mode outputs to the F-feature field on the tensor cores and
+ * ADDs the sums into partials_dev ([nslots][F][nsums][2]) without materialising the field (uq.py:333-343 with a POD
+ * surrogate).  'block' indices: pass F = 1 with u_dev = trapz weights applied to U, mean_dev = trapz(mean). */
+int bk_pod_sobol_accumulate(const double* ymodes_dev, long count, int p, int m, int second_order,
+                            const double* u_dev, const double* mean_dev, int F, const double* shift_dev,
+                            double* partials_dev, void* stream);
 /* Same sums from a user-supplied output sample (ensemble mode, uq.py:336-339):
  * y_dev is the block-major (nblocks*N) x F output design restricted to base rows
  * [row_lo,row_lo+count): element (block b, row k, feature f) at y_dev[(b*ld_block + k)*F + f]. */

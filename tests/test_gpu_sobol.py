@@ -208,3 +208,39 @@ def test_sobol_full_size_cfg2_properties():
     assert np.max(np.abs(uq.details['ST_jansen'][0] - st_)) < 0.01
     assert np.all(st_ > s1 - 0.01)
     assert s2.shape == (8, 8) and np.allclose(s2, s2.T) and np.all(np.diag(s2) == 0)
+
+
+def test_sobol_block_indices_without_pod():
+    """indices='block' on a 3-output Kriging: trapz over the outputs (uq.py:205-218, 319-324)."""
+    from batman_b200 import SurrogateModel, UQ
+    z, states = load_golden('kernel_default_3out')
+    s = SurrogateModel('kriging', np.array([[0.0] * 3, [1.0] * 3]), None)
+    s.adopt(kriging_from_states(states), z['X_train'])
+    N = 1200
+    A, B = philox.base_samples(11, 0, N, [('uniform', 0.0, 1.0)] * 3)
+    got = UQ(s, dists=['Uniform(0., 1.)'] * 3, nsample=N, indices='block', base_samples=(A, B)).sobol()
+    Y = saltelli.int_func(ogp.evaluate(states, saltelli.design_from_base(A, B))[0])
+    want = saltelli.uq_sobol_aggregate(Y, N, 3, indices='block')
+    for g, w in zip(got, want):
+        np.testing.assert_allclose(g, w, rtol=0, atol=ATOL)
+
+
+@pytest.mark.parametrize('k,m,F', [(1, 3, 3), (1000, 20, 400), (77, 5, 7), (4096, 64, 33)])
+def test_pod_inverse_dmma_kernel(k, m, F):
+    """Pod.inverse_transform on the FP64 tensor cores vs numpy (pod/pod.py:226-228)."""
+    import torch
+    from batman_b200.pod_kernels import pod_inverse
+    rng = np.random.RandomState(k)
+    U, mean, modes = rng.randn(F, m), rng.randn(F) * 10, rng.randn(k, m) * 3
+    got = pod_inverse(torch.from_numpy(mean).cuda(), torch.from_numpy(U).cuda(), torch.from_numpy(modes).cuda()).cpu().numpy()
+    want = opod.inverse_transform(mean, U, modes)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.abs(want).max())
+
+
+def test_pod_inverse_reference_known_answer():
+    """tests/test_pod.py:109-114 of the reference through the device kernel."""
+    from batman_b200 import Pod
+    z, _ = load_golden('pod_inverse')
+    out = Pod(z['mean_snapshot'], z['U']).inverse_transform(z['modes'])
+    np.testing.assert_almost_equal(out, [[40, 43, 41], [41, 47, 42]], decimal=3)
+    np.testing.assert_allclose(out, z['ref_inverse'], rtol=0, atol=1e-12)

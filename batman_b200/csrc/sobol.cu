@@ -1,75 +1,9 @@
-// K6 + K1 + K3: Saltelli design -> surrogate mean -> compensated Sobol' sums, fused.
-//
-// Replaces, for every base row k of the experiment,
-//   ot.SobolIndicesExperiment(dist, N, True).generate()        (uq/uq.py:331-332)
-//   output_design = UQ.func(input_design)  [N(2p+2) predictions] (uq/uq.py:333, 192-203)
-//   the dot products of ot.SaltelliSensitivityAlgorithm          (uq/uq.py:342-349, 367-375)
-//   output_design.var(axis=0)                                    (uq/uq.py:403)
-// One thread owns one base row k: it holds A_k and B_k (read, or generated
-// in-kernel with Philox4x32-10), forms the per-dimension squared terms
-// ta_c = ((A_kc - X_jc)/l_c)^2 and tb_c once per training point and re-sums
-// them per block (A, B, E^i = A with column i from B, C^i = B with column i
-// from A) in scipy-cdist order, so 2p+2 distances cost 4P + (2p+2)P DP
-// instructions instead of (2p+2)*3P.  Outputs never reach HBM: per row they
-// are parked in shared memory, multiplied into the (5 + 6p [+ 2p + p(p-1)/2])
-// Saltelli/Jansen products, tree-reduced across the warp with shuffles and
-// accumulated as (hi, lo) double-double sums; each CTA owns one partial slot
-// (no atomics, bit-reproducible for a fixed grid).
-#include "common.cuh"
-#include "covariance.cuh"
-#include "model.h"
+// Generic Saltelli kernel (any instantiated P; runtime block selection), the reducer over stored outputs, the slot
+// reduction and the estimator finalisation.  Shared device code: sobol_common.cuh; the statically scheduled
+// variant for P <= 12: sobol_static.cu.
+#include "sobol_common.cuh"
 
 namespace bk {
-
-constexpr int SOB_THREADS = 128;
-constexpr int SOB_TJ = 128;       // training rows per stage
-constexpr int SOB_CH = 6;         // design blocks evaluated per pass over the training set
-constexpr int SOB_SLOTS = 148 * 4;
-
-__host__ __device__ inline int sobol_nsums(int p, int second) {
-    return 5 + 6 * p + ((second && p > 2) ? 2 * p + p * (p - 1) / 2 : 0);
-}
-__host__ __device__ inline int sobol_nblocks(int p, int second) { return (second && p > 2) ? 2 * p + 2 : p + 2; }
-
-// ---------------------------------------------------------------- Philox4x32-10 (oracle/philox.py is the CPU twin)
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t out[4]) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-__device__ __forceinline__ double unit_from_words(uint32_t hi, uint32_t lo) {
-    const uint64_t k = ((uint64_t)(hi >> 6) << 26) | (uint64_t)(lo >> 6);
-    return __dmul_rn(__dadd_rn((double)k, 0.5), 0x1p-52);
-}
-__device__ __forceinline__ double marginal(int kind, double a, double b, double u) {
-    if (kind == BK_UNIFORM) return __dadd_rn(a, __dmul_rn(__dadd_rn(b, -a), u));   // a + (b - a) * u
-    return __dadd_rn(a, __dmul_rn(b, normcdfinv(u)));                              // mu + sigma * ndtri(u)
-}
-template <int P>
-__device__ __forceinline__ void design_row(uint64_t seed, uint64_t row, int p, int stream, const int* kind,
-                                           const double* pa, const double* pb, double x[P]) {
-#pragma unroll
-    for (int cp = 0; cp < P / 2; ++cp) {
-        if (2 * cp < p) {
-            uint32_t w[4];
-            philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)cp, (uint32_t)stream, (uint32_t)seed,
-                          (uint32_t)(seed >> 32), w);
-            x[2 * cp] = marginal(kind[2 * cp], pa[2 * cp], pb[2 * cp], unit_from_words(w[0], w[1]));
-            x[2 * cp + 1] = (2 * cp + 1 < p)
-                                ? marginal(kind[2 * cp + 1], pa[2 * cp + 1], pb[2 * cp + 1], unit_from_words(w[2], w[3]))
-                                : 0.0;
-        } else {
-            x[2 * cp] = 0.0;
-            x[2 * cp + 1] = 0.0;
-        }
-    }
-}
 
 struct DesignParams {
     uint64_t seed;
@@ -86,88 +20,6 @@ __global__ void k_design_rows(const DesignParams prm) {
     design_row<MAX_P>(prm.seed, (uint64_t)(prm.row_lo + g), prm.p, prm.stream, prm.kind, prm.pa, prm.pb, x);
     for (int c = 0; c < prm.p; ++c) prm.out[g * prm.p + c] = x[c];
 }
-
-// ---------------------------------------------------------------- warp tree reduction + lane-owned dd accumulation
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-// sum index r is owned by lane r%32 of each warp: no races, no atomics
-__device__ __forceinline__ void emit(double v, int& r, int lane, double* wsum_warp) {
-    v = warp_sum(v);
-    if (lane == (r & 31)) {
-        dd a{wsum_warp[2 * r], wsum_warp[2 * r + 1]};
-        dd_add_d(a, v);
-        wsum_warp[2 * r] = a.hi;
-        wsum_warp[2 * r + 1] = a.lo;
-    }
-    ++r;
-}
-
-// products of one base row; ys(b) returns the shifted output of block b for this thread's row
-template <typename YS>
-__device__ __forceinline__ void saltelli_products(YS ys, int p, int second, int lane, double* wsum_warp) {
-    int r = 0;
-    const double yA = ys(0), yB = ys(1);
-    emit(yA, r, lane, wsum_warp);
-    emit(yB, r, lane, wsum_warp);
-    emit(__dmul_rn(yA, yA), r, lane, wsum_warp);
-    emit(__dmul_rn(yB, yB), r, lane, wsum_warp);
-    emit(__dmul_rn(yA, yB), r, lane, wsum_warp);
-    for (int i = 0; i < p; ++i) {
-        const double yE = ys(2 + i);
-        emit(yE, r, lane, wsum_warp);
-        emit(__dmul_rn(yE, yE), r, lane, wsum_warp);
-        emit(__dmul_rn(yB, yE), r, lane, wsum_warp);
-        emit(__dmul_rn(yA, yE), r, lane, wsum_warp);
-        const double dB = __dadd_rn(yB, -yE), dA = __dadd_rn(yA, -yE);
-        emit(__dmul_rn(dB, dB), r, lane, wsum_warp);      // Jansen first order
-        emit(__dmul_rn(dA, dA), r, lane, wsum_warp);      // Jansen total order
-    }
-    if (second) {
-        if (p > 2) {
-            for (int j = 0; j < p; ++j) {
-                const double yC = ys(2 + p + j);
-                emit(yC, r, lane, wsum_warp);
-                emit(__dmul_rn(yC, yC), r, lane, wsum_warp);
-            }
-            for (int i = 0; i < p; ++i)
-                for (int j = 0; j < i; ++j) emit(__dmul_rn(ys(2 + i), ys(2 + p + j)), r, lane, wsum_warp);
-        }
-        // p == 2: C^0 == E^1 and C^1 == E^0, the product sum(yE^1 yC^0) is sum(yE^1 yE^1): no extra sums
-    }
-}
-
-// CTA epilogue: fixed-order sum of the warps' (hi, lo) sums, ADDED into this CTA's slot
-__device__ __forceinline__ void flush_slot(const double* wsum, int nwarps, int nsums, double* slot) {
-    for (int r = threadIdx.x; r < nsums; r += blockDim.x) {
-        dd t{slot[2 * r], slot[2 * r + 1]};
-        for (int w = 0; w < nwarps; ++w) t = dd_add(t, dd{wsum[(w * nsums + r) * 2], wsum[(w * nsums + r) * 2 + 1]});
-        slot[2 * r] = t.hi;
-        slot[2 * r + 1] = t.lo;
-    }
-}
-
-template <int P>
-struct SobolParams {
-    const double* a;       // count x p explicit base samples, or null -> Philox
-    const double* b;
-    uint64_t seed;
-    int mkind[P];
-    double mpa[P], mpb[P];
-    long row_lo, count;
-    int p, second, nb, nsums;
-    int n_pad;
-    const double* xs;
-    const double* alpha;
-    double scale[P], mn[P], ls[P];
-    double c0, c1, y_mean, y_std, shift;
-    double* partial;       // slot 0 of this output; slots are slot_stride doubles apart
-    long slot_stride;
-    double* yout;          // if set: write the (unshifted) outputs [nb][count][m] instead of reducing them
-    int m, q;
-};
 
 template <int KIND, int P>
 __global__ void __launch_bounds__(SOB_THREADS) k_sobol(const SobolParams<P> prm) {
@@ -323,6 +175,10 @@ static int launch_sobol_kp(const bk_gp_s* h, int q, const double* a, const doubl
     prm.partial = partials ? partials + (size_t)q * prm.nsums * 2 : nullptr;
     prm.yout = yout; prm.m = h->m; prm.q = q;
     const size_t smem = ((size_t)2 * SOB_TJ * P + 2 * SOB_TJ + (size_t)prm.nb * SOB_THREADS + 4 * prm.nsums * 2) * 8 + 16;
+    if constexpr (P <= 12) {
+        const int rc = launch_sobol_static<P>(KIND, prm, smem, st);
+        if (rc >= 0) return rc;
+    }
     BK_CUDA(cudaFuncSetAttribute(k_sobol<KIND, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope prof(PROF_SOBOL, st);
     k_sobol<KIND, P><<<SOB_SLOTS, SOB_THREADS, smem, st>>>(prm);

@@ -125,12 +125,52 @@ class DeviceModel:
                                               ws_bytes, current_stream_ptr()))
         return mean, std
 
+    E2E_CHUNK = 8 * 148 * 128 * 8        # rows per pipelined slice (8 K* chunks)
+
     def predict(self, points, return_std=True):
-        """numpy in, numpy out (the Kriging.evaluate boundary): host<->device copies included."""
+        """numpy in, numpy out (the Kriging.evaluate boundary): host<->device copies included.
+
+        Large batches are pipelined: while slice c is being predicted, slice c+1 is uploaded on a copy stream
+        and the results of slice c-1 are downloaded on another (the download blocks the host thread only, the
+        GPU already has the next slice's kernels queued)."""
         points = np.ascontiguousarray(points, dtype=np.float64)
+        k = points.shape[0]
+        src = torch.from_numpy(points)
         with torch.cuda.device(self.device):
-            pts = torch.from_numpy(points).to(self.device, non_blocking=False)
-            mean, std = self.predict_device(pts, return_std)
-            mean = mean.cpu().numpy()
-            std = std.cpu().numpy() if std is not None else None
-        return mean, std
+            if k <= self.E2E_CHUNK:
+                pts = src.to(self.device, non_blocking=False)
+                mean, std = self.predict_device(pts, return_std)
+                return mean.cpu().numpy(), (std.cpu().numpy() if std is not None else None)
+            out_mean = np.empty((k, self.m))
+            out_std = np.empty((k, self.m)) if return_std else None
+            s_main = torch.cuda.current_stream()
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            bounds = [(lo, min(lo + self.E2E_CHUNK, k)) for lo in range(0, k, self.E2E_CHUNK)]
+            pending = None
+            for c in range(len(bounds) + 1):
+                if c < len(bounds):
+                    lo, hi = bounds[c]
+                    with torch.cuda.stream(s_in):
+                        pts = src[lo:hi].to(self.device, non_blocking=True)
+                        ev_in = torch.cuda.Event()
+                        ev_in.record(s_in)
+                    s_main.wait_event(ev_in)
+                    pts.record_stream(s_main)
+                    mean, std = self.predict_device(pts, return_std)
+                    ev = torch.cuda.Event()
+                    ev.record(s_main)
+                    nxt = (lo, hi, mean, std, ev)
+                else:
+                    nxt = None
+                if pending is not None:
+                    plo, phi, pmean, pstd, pev = pending
+                    with torch.cuda.stream(s_out):
+                        s_out.wait_event(pev)
+                        pmean.record_stream(s_out)
+                        torch.from_numpy(out_mean[plo:phi]).copy_(pmean)
+                        if pstd is not None:
+                            pstd.record_stream(s_out)
+                            torch.from_numpy(out_std[plo:phi]).copy_(pstd)
+                pending = nxt
+            s_main.synchronize()
+        return out_mean, out_std

@@ -137,6 +137,11 @@ class SurrogateModel:
         if points.shape[1] != n_features:
             raise ValueError("X has %d features, but MinMaxScaler is expecting %d features as input."
                              % (points.shape[1], n_features))
+        if self.pod is None:
+            # numpy in / numpy out with the copies pipelined against the kernels (DeviceModel.predict)
+            self.predictor.set_input_scaler(self.scaler.scale_, self.scaler.min_)
+            mean, sigma = self.predictor._model().predict(points, return_std=True)
+            return np.atleast_2d(mean), sigma
         pts = torch.from_numpy(np.ascontiguousarray(points)).cuda()
         mean, sigma = self.predict_device(pts, return_std=True)
         return np.atleast_2d(mean.cpu().numpy()), sigma.cpu().numpy()

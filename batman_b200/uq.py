@@ -25,6 +25,20 @@ import numpy as np
 from . import _lib, distributions
 
 
+def shard_rows(size, world, rank):
+    """Base rows of rank `rank`: contiguous slab [lo, hi); the slabs partition [0, size)."""
+    return rank * size // world, (rank + 1) * size // world
+
+
+def allreduce_totals(totals):
+    """Sum the per-rank (hi, lo) Saltelli totals over all ranks -- the path's only collective
+    (NCCL over NVLink for CUDA tensors; gloo in the CPU tests)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(totals, op=dist.ReduceOp.SUM)
+    return totals
+
+
 class UQ:
     """Uncertainty Quantification class (Sobol' part)."""
 
@@ -127,7 +141,7 @@ class UQ:
 
         if self.surrogate is not None:
             size = int(self.points_sample)
-            lo, hi = rank * size // world, (rank + 1) * size // world
+            lo, hi = shard_rows(size, world, rank)
             kinds = _lib.as_int_array(self.marg_kinds)
             params = _lib.as_double_array(self.marg_params)
             A_all = B_all = None
@@ -192,7 +206,7 @@ class UQ:
         totals = torch.empty((F, nsums, 2), dtype=torch.float64, device=dev)
         _lib.check(lib.bk_sobol_reduce_slots(ptr(partials), F, nsums, ptr(totals), stream))
         if world > 1:
-            dist.all_reduce(totals, op=dist.ReduceOp.SUM)       # the path's only collective
+            allreduce_totals(totals)
         out = torch.empty(lib.bk_sobol_result_len(p, F), dtype=torch.float64, device=dev)
         _lib.check(lib.bk_sobol_finalize(ptr(totals), size, p, F, second, ptr(out), stream))
         res = out.cpu().numpy()

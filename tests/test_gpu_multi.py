@@ -1,0 +1,57 @@
+"""GPU, 2 ranks (skipped on a single-GPU box): sharded UQ.sobol + NCCL all-reduce == single-GPU result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _worker(rank, world, port, N, q):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    import torch
+    import torch.distributed as dist
+    from conftest import kriging_from_states, load_golden
+    from batman_b200 import SurrogateModel, UQ
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    z, states = load_golden('ishigami_n100')
+    s = SurrogateModel('kriging', z['corners'], None)
+    s.adopt(kriging_from_states(states), z['X_raw'])
+    uq = UQ(s, dists=['Uniform(-3.141592653589793, 3.141592653589793)'] * 3, nsample=N)
+    res = uq.sobol()
+    if rank == 0:
+        q.put([np.asarray(r) for r in res])
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sobol_matches_single_gpu():
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from conftest import kriging_from_states, load_golden
+    from batman_b200 import SurrogateModel, UQ
+    N = 50001
+    with socket.socket() as sck:
+        sck.bind(('127.0.0.1', 0))
+        port = sck.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, N, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    z, states = load_golden('ishigami_n100')
+    s = SurrogateModel('kriging', z['corners'], None)
+    s.adopt(kriging_from_states(states), z['X_raw'])
+    want = UQ(s, dists=['Uniform(-3.141592653589793, 3.141592653589793)'] * 3, nsample=N).sobol()
+    for g, w in zip(got, want):
+        np.testing.assert_allclose(g, w, rtol=0, atol=1e-12)

@@ -136,6 +136,21 @@ def test_edge_cases():
     np.testing.assert_array_equal(sb[-len(s0):], s0)
 
 
+def test_pipelined_host_path_equals_single_shot(monkeypatch):
+    """Large numpy batches go through the copy/compute pipeline: results must be bit-identical."""
+    from batman_b200.device_model import DeviceModel
+    z, states = load_golden('kernel_default_3out')
+    k = kriging_from_states(states)
+    pts = np.tile(z['points'], (60, 1))
+    m0, s0 = k.evaluate(pts)
+    monkeypatch.setattr(DeviceModel, 'E2E_CHUNK', 700)          # 3360 rows -> 5 slices, last one ragged
+    m1, s1 = k.evaluate(pts)
+    np.testing.assert_array_equal(m0, m1)
+    np.testing.assert_array_equal(s0, s1)
+    m2 = k.evaluate(pts, return_std=False)
+    np.testing.assert_array_equal(m0, m2)
+
+
 def test_pickle_roundtrip_drops_device_buffers():
     import pickle
     z, states = load_golden('kernel_default_3out')

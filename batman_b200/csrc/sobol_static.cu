@@ -63,7 +63,7 @@ __device__ __forceinline__ void ss_pass(StaticCtx<P>& cx, const double (&ua)[P],
         mbar_wait(&cx.bar[s], (uint32_t)((cx.tctr >> 1) & 1));
         const double* xrow = cx.xs_s + s * SOB_TJ * P;
         const double* arow = cx.al_s + s * SOB_TJ;
-#pragma unroll 1
+#pragma unroll 2   // two training rows in flight: 2 x CNT independent sqrt/exp chains for ptxas to interleave
         for (int j = 0; j < SOB_TJ; ++j) {
             double ta[P], tb[P];
 #pragma unroll

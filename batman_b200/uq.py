@@ -88,13 +88,52 @@ class UQ:
             self.init_size = len(space)
             data = np.asarray(data, dtype=np.float64)
             self.output_len = data.shape[1]
-            self.output = data
+            self._output = data
             self.points_sample = self.init_size
         if (xdata is None) and (self.output_len > 1):
             self.xdata = np.linspace(0, 1, self.output_len)
         else:
             self.xdata = xdata
         self.details = None
+        self._sample = None
+        if surrogate is not None:
+            self._output = None
+
+    # ------------------------------------------------------------------ LHS propagation sample (uq.py:159-173)
+    @property
+    def sample(self):
+        """N-point randomised LHS of the joint distribution (``ot.LHSExperiment(dist, N, True, True)``,
+        uq.py:159-160), drawn lazily with numpy (seeded) -- OpenTURNS' stream cannot be reproduced."""
+        if self._sample is None and self.surrogate is not None:
+            from scipy.special import ndtri
+            rng = np.random.RandomState(self.seed)
+            n, p = int(self.points_sample), self.p_len
+            u = np.empty((n, p))
+            for j in range(p):
+                u[:, j] = (rng.permutation(n) + rng.rand(n)) / n        # shuffled cells, random shift
+            x = np.empty_like(u)
+            for j in range(p):
+                a, b = self.marg_params[2 * j], self.marg_params[2 * j + 1]
+                x[:, j] = a + (b - a) * u[:, j] if self.marg_kinds[j] == distributions.UNIFORM else a + b * ndtri(u[:, j])
+            self._sample = x
+        return self._sample if self.surrogate is not None else self.space
+
+    @property
+    def output(self):
+        """Surrogate mean on the LHS sample (uq.py:173), evaluated on the device on first use."""
+        if self._output is None and self.surrogate is not None:
+            self._output = self.func(self.sample)
+        return self._output
+
+    @output.setter
+    def output(self, value):
+        self._output = value
+
+    def moments(self):
+        """Mean and standard deviation of every output over the LHS sample (what error_propagation
+        plots, uq.py:501-529)."""
+        out = np.asarray(self.output, dtype=np.float64)
+        return out.mean(axis=0), out.std(axis=0)
 
     def __repr__(self):
         return ("UQ object: Method({}), Input({}), Distribution({})"

@@ -134,6 +134,21 @@ def measure_dgemm_peak(torch):
     return 2 * n ** 3 / best * 1e-12
 
 
+def ncu_traffic_bytes():
+    """DRAM bytes of one k_var_trmm launch from the committed ncu capture (None if the summary is absent)."""
+    path = os.path.join(ROOT, 'profiles', 'r01_ncu_v2', 'k_var_trmm_summary.csv')
+    scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    try:
+        total = 0.0
+        for line in open(path):
+            f = line.strip().split(',')
+            if f[0] in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
+                total += float(f[2]) * scale[f[1]]
+        return total or None
+    except Exception:
+        return None
+
+
 def cpu_reference(steps, warmup, sample_rows, per_point_rows, design_rows):
     """Reference CPU path on the host cores (oracle/sk_reference.py): -> dict for the JSON line."""
     from threadpoolctl import threadpool_info
@@ -314,7 +329,10 @@ def main():
     achieved = algo_flops_per_pred * rows_per_launch / (var_ms / max(1, var_launches) * 1e-3) * 1e-12
     peak = measure_dgemm_peak(torch)
     roofline = {"bound": "tensor", "kernel": "k_var_trmm (FP64 DMMA)", "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(),
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_var_trmm launch (151552 points), "
+                                  "ncu --set full capture in profiles/r01_ncu_v2/k_var_trmm_summary.csv; algorithmic bytes "
+                                  "per launch = K* chunk + W = %.3e" % (151552 * N_TRAIN * 8 + N_TRAIN * N_TRAIN * 8),
                 "peak_source": "measured live: torch.matmul fp64 8192^3 best of 10 (cuBLAS DGEMM); MEASURED_PEAKS.json "
                                "has no FP64 entry; raw DMMA pipe rate 37.1 TFLOP/s in profiles/r01_fp64_peaks.jsonl",
                 "algorithmic_flops_per_prediction": algo_flops_per_pred,

@@ -77,9 +77,10 @@ EPS = np.finfo(np.float64).eps
 @pytest.mark.parametrize('n,p,kind,ls', [(1024, 8, 'matern32', 0.7), (1024, 8, 'matern32', 3.0),
                                          (700, 5, 'matern52', 1.0), (333, 3, 'rbf', 0.12),
                                          (256, 10, 'matern12', 2.0), (513, 20, 'rbf', 2.5),
-                                         (333, 3, 'rbf', 0.4)])
+                                         (333, 3, 'rbf', 0.4), (4096, 10, 'matern32', 1.0)])
 def test_synthetic_parity_vs_oracle_and_longdouble(n, p, kind, ls):
-    """Sizes the oracle finishes in seconds; ragged n (not a multiple of 128) and k (not of 256).
+    """Sizes the oracle finishes in seconds (n = 4096 is BASELINE config 3's model size); ragged n (not a
+    multiple of 128) and k (not of 256).
 
     The mean is a sign-alternating sum sum_j k_j alpha_j; its conditioning
     A = sum|k_j alpha_j| * y_std / scale is reported next to the error.  The

@@ -40,6 +40,25 @@ def normalise_y(y):
     return (y - mean) / std, mean, std
 
 
+def _world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(), dist.get_rank()
+    return 1, 0
+
+
+def _shared_seed(device):
+    """One integer drawn on rank 0 and broadcast: the (unseeded, kriging.py:170-171) DE runs must walk the
+    same trajectory on every rank for the sharded objective to make sense."""
+    import torch
+    import torch.distributed as dist
+    world, _ = _world()
+    seed = torch.tensor([np.random.randint(0, 2 ** 31 - 1)], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.broadcast(seed, src=0)
+    return int(seed.item())
+
+
 class _Objective:
     def __init__(self, kernel, X_dev, y_dev, dim):
         self.kernel, self.X_dev, self.y_dev, self.dim = kernel, X_dev, y_dev, dim
@@ -49,10 +68,30 @@ class _Objective:
         return [kernel_spec.flatten(self.kernel.clone_with_theta(t), self.dim) for t in thetas]
 
     def neg_lml(self, thetas):
-        """thetas (R, n_theta) -> -LML (R,), +inf where the Cholesky fails (sklearn:_gpr.py:591-593)."""
+        """thetas (R, n_theta) -> -LML (R,), +inf where the Cholesky fails (sklearn:_gpr.py:591-593).
+
+        With torch.distributed initialised the R candidates (a DE generation, or the finite-difference stencil
+        of an L-BFGS-B restart) are sharded over the ranks -- each GPU factorises its slice -- and the values
+        are all-gathered, so every rank sees the same objective and the optimisers stay in lockstep."""
         thetas = np.atleast_2d(thetas)
         self.n_evals += len(thetas)
-        return -lml_batched(self.X_dev, self.y_dev, self.specs(thetas))
+        world, rank = _world()
+        if world == 1 or len(thetas) < world:
+            return -lml_batched(self.X_dev, self.y_dev, self.specs(thetas))
+        import torch
+        import torch.distributed as dist
+        lo, hi = rank * len(thetas) // world, (rank + 1) * len(thetas) // world
+        mine = -lml_batched(self.X_dev, self.y_dev, self.specs(thetas[lo:hi]))
+        per = (len(thetas) + world - 1) // world
+        buf = torch.full((per,), float('nan'), dtype=torch.float64, device=self.X_dev.device)
+        buf[:hi - lo] = torch.from_numpy(mine).to(self.X_dev.device)
+        gathered = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(gathered, buf)
+        out = np.empty(len(thetas))
+        for r in range(world):
+            rlo, rhi = r * len(thetas) // world, (r + 1) * len(thetas) // world
+            out[rlo:rhi] = gathered[r][:rhi - rlo].cpu().numpy()
+        return out
 
 
 def optimise_theta(kernel, X_dev, y_dev, dim, global_optimizer, n_restarts_local):
@@ -63,9 +102,10 @@ def optimise_theta(kernel, X_dev, y_dev, dim, global_optimizer, n_restarts_local
     obj = _Objective(kernel, X_dev, y_dev, dim)
     if global_optimizer:
         best = None
+        seed = _shared_seed(X_dev.device)
         for i in range(3):                                           # kriging.py:176-177 (n_restart = 3)
             res = differential_evolution(lambda th: obj.neg_lml(th.T), bounds, tol=0.001, popsize=15 + i,
-                                         vectorized=True, updating='deferred', polish=False)
+                                         vectorized=True, updating='deferred', polish=False, seed=seed + i)
             # scipy's default polish (L-BFGS-B on the best member) with batched central differences
             res = _lbfgs(obj, res.x, bounds, fallback=res)
             if best is None or res.fun < best.fun:
@@ -76,7 +116,8 @@ def optimise_theta(kernel, X_dev, y_dev, dim, global_optimizer, n_restarts_local
         if not np.isfinite(bounds).all():
             raise ValueError("Multiple optimizer restarts (n_restarts_optimizer>0) requires that all "
                              "bounds are finite.")                    # sklearn:_gpr.py:313-317
-        starts += [np.random.uniform(bounds[:, 0], bounds[:, 1]) for _ in range(n_restarts_local)]
+        rng = np.random.RandomState(_shared_seed(X_dev.device)) if _world()[0] > 1 else np.random
+        starts += [rng.uniform(bounds[:, 0], bounds[:, 1]) for _ in range(n_restarts_local)]
     best = None
     for s in starts:
         res = _lbfgs(obj, s, bounds)

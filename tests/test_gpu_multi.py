@@ -55,3 +55,50 @@ def test_two_gpu_sobol_matches_single_gpu():
     want = UQ(s, dists=['Uniform(-3.141592653589793, 3.141592653589793)'] * 3, nsample=N).sobol()
     for g, w in zip(got, want):
         np.testing.assert_allclose(g, w, rtol=0, atol=1e-12)
+
+
+def _fit_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    from batman_b200 import Kriging
+    from oracle import functions as ofun
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    X = ofun.halton(48, 2)
+    y = ofun.michalewicz(np.pi * X)
+    k = Kriging(X, y)                                  # DE generations sharded over the ranks
+    q.put((rank, np.asarray(k.hyperparameter[0]), k.gp_models[0].log_marginal_likelihood_value_))
+    dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_restarts_agree_across_ranks():
+    """Hyper-parameter candidates shard across ranks (all-gather of LML values): every rank must end on
+    the same theta, and it must be at least as good as scikit-learn's multi-restart optimum."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import ConstantKernel, Matern
+    from oracle import functions as ofun
+    with socket.socket() as sck:
+        sck.bind(('127.0.0.1', 0))
+        port = sck.getsockname()[1]
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_fit_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    np.testing.assert_array_equal(res[0][1], res[1][1])
+    assert res[0][2] == res[1][2]
+    X = ofun.halton(48, 2)
+    y = ofun.michalewicz(np.pi * X)
+    ref = GaussianProcessRegressor(kernel=ConstantKernel() * Matern(length_scale=(1.0, 1.0), length_scale_bounds=[(0.01, 100)] * 2),
+                                   normalize_y=True, n_restarts_optimizer=20, random_state=0).fit(X, y[:, 0])
+    assert res[0][2] >= ref.log_marginal_likelihood_value_ - 1e-3

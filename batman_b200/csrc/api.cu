@@ -1,4 +1,5 @@
 // extern "C" entry points of libbatman_b200.so (declared in include/batman_b200.h).
+#include <math.h>
 #include <stdarg.h>
 
 #include <new>
@@ -39,7 +40,10 @@ ProfScope::~ProfScope() {
 }
 
 // kernels (other translation units)
-int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar, cudaStream_t st);
+int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar, int8_t* kq,
+                   double kappa, cudaStream_t st);
+int launch_var_ozaki(const bk_gp_s* h, int q, const int8_t* kq, double kappa, long k, double* std_out,
+                     double* scratch, int* fail_flag, cudaStream_t st);
 int launch_var(const bk_gp_s* h, int q, const double* kstar, long k, double* std_out, cudaStream_t st);
 int launch_pack_w(const double* w, int n, double* out, cudaStream_t st);
 int launch_sobol(const bk_gp_s* h, int q, const double* a, const double* b, uint64_t seed, const int* mkind,
@@ -62,9 +66,10 @@ int lml_batched(const double* X, const double* y, int n, int p, int R, const int
                 const double* c1, const double* kdiag, const double* ls, double* lml_out, void* ws, size_t ws_bytes,
                 cudaStream_t st);
 int gp_factorise(const double* X, const double* y, int n, int p, int kind, double c0, double c1, double kdiag,
-                 const double* ls, double* L_out, double* alpha_out, double* wt_tiles_out, double* lml_out,
-                 int* info_out, void* ws, size_t ws_bytes, cudaStream_t st);
-int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, void* ws, size_t ws_bytes, cudaStream_t st);
+                 const double* ls, double* L_out, double* alpha_out, double* wt_tiles_out, int8_t* wq_out,
+                 double* wsig_out, double* lml_out, int* info_out, void* ws, size_t ws_bytes, cudaStream_t st);
+int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, int8_t* wq_out, double* wsig_out, void* ws,
+                     size_t ws_bytes, cudaStream_t st);
 int sobol_nsums_host(int p, int second);
 int sobol_nslots_host();
 
@@ -167,13 +172,41 @@ int bk_pack_w(const double* w_dev, int n, double* w_tiles_dev, void* stream) {
     return launch_pack_w(w_dev, n, w_tiles_dev, (cudaStream_t)stream);
 }
 
+static double pow2_at_least(double v) {
+    int e = 0;
+    if (!(v > 0.0)) return 1.0;
+    frexp(v, &e);
+    return ldexp(1.0, e);
+}
+
+// per point: K* tile bytes (FP64 fragments or 8 int8 slices: both n_pad * 8) + 1 KiB of pass-0 scratch (int8 path)
+static size_t predict_bytes_per_point(const bk_gp_s* h) { return (size_t)h->n_pad * sizeof(double) + 1024; }
+
 size_t bk_gp_predict_workspace(bk_gp_t h, long k, int want_std) {
     if (!h || !want_std || k <= 0) return 0;
     long kk = (k + PRED_CHUNK_ALIGN - 1) / PRED_CHUNK_ALIGN * PRED_CHUNK_ALIGN;
     const long cap = 148L * TILE_T * 8;   // 8 test tiles per SM per chunk: 16 warps/SM for K1, 8 waves for K2
     if (kk > cap) kk = cap;
-    return (size_t)kk * h->n_pad * sizeof(double);
+    return (size_t)kk * predict_bytes_per_point(h) + 256;
 }
+
+int bk_gp_set_output_int8(bk_gp_t h, int q, const int8_t* wq_dev, const double* wsig_dev) {
+    if (!h) return set_error("bk_gp_set_output_int8: NULL handle");
+    if (q < 0 || q >= h->m) return set_error("bk_gp_set_output_int8: output %d out of range [0, %d)", q, h->m);
+    h->out[q].wq = wq_dev;
+    h->out[q].wsig = wsig_dev;
+    return 0;
+}
+
+int bk_gp_set_var_mode(bk_gp_t h, int mode) {
+    if (!h) return set_error("bk_gp_set_var_mode: NULL handle");
+    if (mode != 0 && mode != 1) return set_error("bk_gp_set_var_mode: mode must be 0 (FP64 DMMA) or 1 (int8 tcgen05)");
+    if (mode == 1 && h->n_pad > 16384) return set_error("bk_gp_set_var_mode: int32 accumulation is exact only for n_train <= 16384");
+    h->var_mode = mode;
+    return 0;
+}
+
+size_t bk_gp_wq_bytes(int n_train) { return (size_t)padded_n(n_train) * padded_n(n_train) * 8; }
 
 int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, double* std_dev, void* workspace_dev,
                   size_t workspace_bytes, void* stream) {
@@ -184,20 +217,32 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
     cudaStream_t st = (cudaStream_t)stream;
     if (!std_dev) {
         for (int q = 0; q < h->m; ++q)
-            if (int rc = launch_predict(h, q, pts_dev, k, mean_dev, nullptr, st)) return rc;
+            if (int rc = launch_predict(h, q, pts_dev, k, mean_dev, nullptr, nullptr, 1.0, st)) return rc;
         return 0;
     }
-    const size_t per_point = (size_t)h->n_pad * sizeof(double);
-    long chunk = (long)(workspace_bytes / per_point) / PRED_CHUNK_ALIGN * PRED_CHUNK_ALIGN;
+    const size_t per_point = predict_bytes_per_point(h);
+    long chunk = workspace_bytes > 256 ? (long)((workspace_bytes - 256) / per_point) / PRED_CHUNK_ALIGN * PRED_CHUNK_ALIGN : 0;
     if (!workspace_dev || chunk < PRED_CHUNK_ALIGN)
         return set_error("bk_gp_predict: sigma needs a workspace of at least %zu bytes (got %zu)",
-                         per_point * PRED_CHUNK_ALIGN, workspace_bytes);
-    double* kstar = (double*)workspace_dev;
+                         per_point * PRED_CHUNK_ALIGN + 256, workspace_bytes);
+    char* ws = (char*)workspace_dev;
+    double* kstar = (double*)ws;                                               // or the int8 slices: same footprint
+    double* scratch = (double*)(ws + (size_t)chunk * h->n_pad * sizeof(double));
+    int* fail_flag = (int*)(ws + ((workspace_bytes - 256) & ~(size_t)7));      // tail of the caller's workspace
     for (long lo = 0; lo < k; lo += chunk) {
         const long cnt = (k - lo) < chunk ? (k - lo) : chunk;
         for (int q = 0; q < h->m; ++q) {
-            if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, kstar, st)) return rc;
-            if (int rc = launch_var(h, q, kstar, cnt, std_dev + lo * h->m, st)) return rc;
+            if (h->var_mode == 1) {
+                const GpOutput& o = h->out[q];
+                const double kappa = pow2_at_least(fabs(o.c0) + fabs(o.c1));   // |k| <= |c0| + |c1| (stationary factor <= 1)
+                if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, nullptr, (int8_t*)kstar,
+                                            kappa, st)) return rc;
+                if (int rc = launch_var_ozaki(h, q, (const int8_t*)kstar, kappa, cnt, std_dev + lo * h->m, scratch,
+                                              fail_flag, st)) return rc;
+            } else {
+                if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, kstar, nullptr, 1.0, st)) return rc;
+                if (int rc = launch_var(h, q, kstar, cnt, std_dev + lo * h->m, st)) return rc;
+            }
         }
     }
     return 0;
@@ -219,17 +264,19 @@ int bk_lml_batched(const double* x_dev, const double* y_dev, int n_train, int p,
 
 int bk_gp_factorise(const double* x_dev, const double* y_dev, int n_train, int p, int kind, double c0, double c1,
                     double kdiag, const double* ls_host, double* l_dev, double* alpha_dev, double* w_tiles_dev,
-                    double* lml_dev, int* info_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+                    int8_t* wq_dev, double* wsig_dev, double* lml_dev, int* info_dev, void* workspace_dev,
+                    size_t workspace_bytes, void* stream) {
     if (!x_dev || !y_dev || !ls_host || !l_dev || !alpha_dev || !lml_dev || !info_dev || !workspace_dev)
         return set_error("bk_gp_factorise: NULL pointer");
-    return gp_factorise(x_dev, y_dev, n_train, p, kind, c0, c1, kdiag, ls_host, l_dev, alpha_dev, w_tiles_dev, lml_dev,
-                        info_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+    return gp_factorise(x_dev, y_dev, n_train, p, kind, c0, c1, kdiag, ls_host, l_dev, alpha_dev, w_tiles_dev, wq_dev,
+                        wsig_dev, lml_dev, info_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }
 
-int bk_tri_inverse_pack(const double* l_dev, int n_train, double* w_tiles_dev, void* workspace_dev,
-                        size_t workspace_bytes, void* stream) {
+int bk_tri_inverse_pack(const double* l_dev, int n_train, double* w_tiles_dev, int8_t* wq_dev, double* wsig_dev,
+                        void* workspace_dev, size_t workspace_bytes, void* stream) {
     if (!l_dev || !w_tiles_dev || !workspace_dev) return set_error("bk_tri_inverse_pack: NULL pointer");
-    return tri_inverse_pack(l_dev, n_train, w_tiles_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+    return tri_inverse_pack(l_dev, n_train, w_tiles_dev, wq_dev, wsig_dev, workspace_dev, workspace_bytes,
+                            (cudaStream_t)stream);
 }
 
 int bk_sobol_nsums(int p, int second_order) { return sobol_nsums_host(p, second_order); }

@@ -35,9 +35,12 @@ struct PredictParams {
     double* mean;          // k x ld, column q
     int ld, q;
     double* kstar;         // packed tiles [T][n_pad/16][2048] or null
+    int8_t* kq;            // int8 slice tiles [T][n_pad/32][8][4096] (WRITE_K == 2)
+    double inv_kappa;      // 1 / (power of two >= max |k|)
 };
 
-template <int KIND, int P, bool WRITE_K>
+// WRITE_K: 0 = mean only, 1 = K* as FP64 DMMA fragment tiles (gp_var.cu), 2 = K* as int8 slices (var_ozaki.cu)
+template <int KIND, int P, int WRITE_K>
 __global__ void __launch_bounds__(PRED_THREADS) k_predict(const PredictParams<P> prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* xs_s = reinterpret_cast<double*>(smem_raw);                 // [2][TJ*P]
@@ -85,7 +88,16 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(const PredictParams<P>
 
     // K* destination of this thread (see gp_var.cu for the tile layout)
     double* kdst[PRED_TP];
-    if constexpr (WRITE_K) {
+    int8_t* qdst[PRED_TP];
+    if constexpr (WRITE_K == 2) {
+#pragma unroll
+        for (int e = 0; e < PRED_TP; ++e) {
+            const long t = t_idx[e];
+            const int r = (int)(t % TILE_T);
+            qdst[e] = prm.kq + (size_t)(t / TILE_T) * (prm.n_pad / 32) * 8 * 4096 + (r >> 3) * 256 + (r & 7) * 16;
+        }
+    }
+    if constexpr (WRITE_K == 1) {
 #pragma unroll
         for (int e = 0; e < PRED_TP; ++e) {
             long t = t_idx[e];
@@ -131,7 +143,30 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(const PredictParams<P>
                     acc[e] = tsum;
                 }
             }
-            if constexpr (WRITE_K) {
+            if constexpr (WRITE_K == 2) {
+                // error-free int8 slicing: k / kappa = sum_a q_a 2^-(7a-1), |q_a| <= 64 (var_ozaki.cu)
+                const int jg = tile * PRED_TJ + j8;
+#pragma unroll
+                for (int e = 0; e < PRED_TP; ++e) {
+                    unsigned long long pk[8];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) pk[a] = 0ull;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        double y = __dmul_rn(__dmul_rn(kbuf[e][jj], prm.inv_kappa), 64.0);
+#pragma unroll
+                        for (int a = 0; a < 8; ++a) {
+                            const double qd = rint(y);
+                            pk[a] |= (unsigned long long)(unsigned char)(signed char)__double2int_rn(qd) << (8 * jj);
+                            y = __dmul_rn(__dadd_rn(y, -qd), 128.0);
+                        }
+                    }
+                    int8_t* d = qdst[e] + (size_t)(jg >> 5) * 8 * 4096 + ((jg & 31) >> 4) * 128 + (jg & 15);
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) *reinterpret_cast<unsigned long long*>(d + (size_t)a * 4096) = pk[a];
+                }
+            }
+            if constexpr (WRITE_K == 1) {
                 const int jg = tile * PRED_TJ + j8;          // global train index of kbuf[.][0]
 #pragma unroll
                 for (int e = 0; e < PRED_TP; ++e) {
@@ -163,7 +198,7 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(const PredictParams<P>
 
 template <int KIND, int P>
 static int launch_predict_kp(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar,
-                             cudaStream_t st) {
+                             int8_t* kq, double kappa, cudaStream_t st) {
     const GpOutput& o = h->out[q];
     PredictParams<P> prm;
     prm.pts = pts; prm.k = k; prm.p = h->p; prm.n_pad = h->n_pad;
@@ -174,18 +209,21 @@ static int launch_predict_kp(const bk_gp_s* h, int q, const double* pts, long k,
         prm.ls[c] = c < h->p ? o.ls[c] : 1.0;
     }
     prm.c0 = o.c0; prm.c1 = o.c1; prm.y_mean = o.y_mean; prm.y_std = o.y_std;
-    prm.mean = mean; prm.ld = h->m; prm.q = q; prm.kstar = kstar;
+    prm.mean = mean; prm.ld = h->m; prm.q = q; prm.kstar = kstar; prm.kq = kq; prm.inv_kappa = 1.0 / kappa;
     const size_t smem = (size_t)2 * PRED_TJ * P * 8 + 2 * PRED_TJ * 8 + 16;
     const long per_cta = PRED_THREADS * PRED_TP;
     // with K* output every 128-point tile must be fully written: round the grid up to whole tiles
     const unsigned grid = (unsigned)((k + per_cta - 1) / per_cta);
     ProfScope prof(PROF_PREDICT, st);
-    if (kstar) {
-        BK_CUDA(cudaFuncSetAttribute(k_predict<KIND, P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_predict<KIND, P, true><<<grid, PRED_THREADS, smem, st>>>(prm);
+    if (kq) {
+        BK_CUDA(cudaFuncSetAttribute(k_predict<KIND, P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_predict<KIND, P, 2><<<grid, PRED_THREADS, smem, st>>>(prm);
+    } else if (kstar) {
+        BK_CUDA(cudaFuncSetAttribute(k_predict<KIND, P, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_predict<KIND, P, 1><<<grid, PRED_THREADS, smem, st>>>(prm);
     } else {
-        BK_CUDA(cudaFuncSetAttribute(k_predict<KIND, P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_predict<KIND, P, false><<<grid, PRED_THREADS, smem, st>>>(prm);
+        BK_CUDA(cudaFuncSetAttribute(k_predict<KIND, P, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_predict<KIND, P, 0><<<grid, PRED_THREADS, smem, st>>>(prm);
     }
     BK_LAUNCH_CHECK("k_predict");
     return 0;
@@ -193,18 +231,18 @@ static int launch_predict_kp(const bk_gp_s* h, int q, const double* pts, long k,
 
 template <int KIND>
 static int launch_predict_k(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar,
-                            cudaStream_t st) {
+                            int8_t* kq, double kappa, cudaStream_t st) {
     switch (h->P) {
-        case 2: return launch_predict_kp<KIND, 2>(h, q, pts, k, mean, kstar, st);
-        case 4: return launch_predict_kp<KIND, 4>(h, q, pts, k, mean, kstar, st);
-        case 6: return launch_predict_kp<KIND, 6>(h, q, pts, k, mean, kstar, st);
-        case 8: return launch_predict_kp<KIND, 8>(h, q, pts, k, mean, kstar, st);
-        case 10: return launch_predict_kp<KIND, 10>(h, q, pts, k, mean, kstar, st);
-        case 12: return launch_predict_kp<KIND, 12>(h, q, pts, k, mean, kstar, st);
-        case 16: return launch_predict_kp<KIND, 16>(h, q, pts, k, mean, kstar, st);
-        case 20: return launch_predict_kp<KIND, 20>(h, q, pts, k, mean, kstar, st);
-        case 24: return launch_predict_kp<KIND, 24>(h, q, pts, k, mean, kstar, st);
-        case 32: return launch_predict_kp<KIND, 32>(h, q, pts, k, mean, kstar, st);
+        case 2: return launch_predict_kp<KIND, 2>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case 4: return launch_predict_kp<KIND, 4>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case 6: return launch_predict_kp<KIND, 6>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case 8: return launch_predict_kp<KIND, 8>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case 10: return launch_predict_kp<KIND, 10>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case 12: return launch_predict_kp<KIND, 12>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case 16: return launch_predict_kp<KIND, 16>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case 20: return launch_predict_kp<KIND, 20>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case 24: return launch_predict_kp<KIND, 24>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case 32: return launch_predict_kp<KIND, 32>(h, q, pts, k, mean, kstar, kq, kappa, st);
     }
     return set_error("unsupported padded dimension %d", h->P);
 }
@@ -225,13 +263,14 @@ int launch_debug_fastmath(const double* in, long n, double* o_sqrt, double* o_ex
 }
 
 // mean of output q at k points; if kstar != null also the packed K* tiles for gp_var
-int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar, cudaStream_t st) {
+int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar, int8_t* kq,
+                   double kappa, cudaStream_t st) {
     switch (h->out[q].kind) {
-        case BK_MATERN12: return launch_predict_k<BK_MATERN12>(h, q, pts, k, mean, kstar, st);
-        case BK_MATERN32: return launch_predict_k<BK_MATERN32>(h, q, pts, k, mean, kstar, st);
-        case BK_MATERN52: return launch_predict_k<BK_MATERN52>(h, q, pts, k, mean, kstar, st);
-        case BK_RBF: return launch_predict_k<BK_RBF>(h, q, pts, k, mean, kstar, st);
-        case BK_MATERN_INF: return launch_predict_k<BK_MATERN_INF>(h, q, pts, k, mean, kstar, st);
+        case BK_MATERN12: return launch_predict_k<BK_MATERN12>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case BK_MATERN32: return launch_predict_k<BK_MATERN32>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case BK_MATERN52: return launch_predict_k<BK_MATERN52>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case BK_RBF: return launch_predict_k<BK_RBF>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case BK_MATERN_INF: return launch_predict_k<BK_MATERN_INF>(h, q, pts, k, mean, kstar, kq, kappa, st);
     }
     return set_error("output %d has no kernel set", q);
 }

@@ -1,5 +1,7 @@
 // Host-side model handle behind the C ABI (include/batman_b200.h).
 #pragma once
+#include <stdint.h>
+
 #include <vector>
 
 #include "../../include/batman_b200.h"
@@ -19,12 +21,15 @@ struct GpOutput {
     const double* xs = nullptr;      // n_pad x P   (X_train / ls, zero padded)
     const double* alpha = nullptr;   // n_pad       (zero padded)
     const double* wt = nullptr;      // packed L^-1 tiles, or null
+    const int8_t* wq = nullptr;      // int8 slices of L^-1 (Ozaki path), or null
+    const double* wsig = nullptr;    // per-row power-of-two scales of the slices
 };
 
 }  // namespace bk
 
 struct bk_gp_s {
     int n = 0, p = 0, P = 0, m = 0, n_pad = 0;
+    int var_mode = 0;                // 0 = FP64 DMMA (k_var_trmm), 1 = int8 tcgen05 (k_var_ozaki)
     double scale[bk::MAX_P];
     double mn[bk::MAX_P];
     std::vector<bk::GpOutput> out;

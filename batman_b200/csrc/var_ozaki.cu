@@ -1,0 +1,288 @@
+// K2' `k_var_ozaki`: the variance TRMM on the 5th-generation tensor cores (tcgen05, int8, TMEM accumulators).
+//
+// tcgen05 has no FP64 kind, so `V = W K*` is evaluated EXACTLY from int8 slices (Ozaki scheme I):
+//     W_ij  = sigma_i * sum_{a=1..8} q_a(i,j) 2^-(7a-1)      sigma_i = power of two >= max_j |W_ij|
+//     K*_jt = kappa   * sum_{b=1..8} p_b(j,t) 2^-(7b-1)      kappa   = power of two >= max |k|,   |q|,|p| <= 64
+//     V_it  = sigma_i kappa * sum_{g=2..9} 2^-(7g-2) D_g(i,t),   D_g = sum_{a+b=g} sum_j q_a p_b
+// D_g is an int32 accumulation of int8 products (exact for n <= 16384); the 36 slice pairs with a+b <= 9
+// reproduce float64 accuracy (profiles/r01_ozaki_feasibility.md).  Same contract as k_var_trmm (gp_var.cu).
+//
+// One CTA = 128 test points.  Per row panel of W (128 rows) the K loop runs TWICE because only four
+// 128x128 int32 accumulator groups fit in TMEM (512 columns): pass 0 = groups 2..5 (slices 1..4, 10 MMAs per
+// 32-wide k slab), pass 1 = groups 6..9 (slices 1..8, 26 MMAs).  The pass-0 combination is parked in an
+// L2-resident scratch tile and added in pass 1.
+//   warp 5 lane 0 : TMA producer  (cp.async.bulk of pre-packed slice tiles, 3-stage full/empty mbarrier ring)
+//   warp 4 lane 0 : MMA issuer    (tcgen05.mma.cta_group::1.kind::i8, M128 N128 K32, SMEM descriptors, commit)
+//   warps 0..3    : epilogue      (tcgen05.ld -> int32 -> FP64 Horner -> v^2 -> column sums)
+// Operand tiles are packed on the producer side (W at upload, K* by K1) in the non-swizzled K-major UMMA
+// layout: element (row r, byte b) of a 128 x 32 B tile at (r/8)*256 + (b/16)*128 + (r%8)*16 + b%16.
+#include "common.cuh"
+#include "model.h"
+
+namespace bk {
+
+constexpr int OZ_S = 8;                       // int8 slices per operand
+constexpr int OZ_TILE = 4096;                 // bytes of one 128 x 32 B slice tile
+constexpr int OZ_STAGES = 3;
+constexpr int OZ_STAGE_BYTES = 2 * OZ_S * OZ_TILE;         // A slices at +0, B slices at +32 KiB
+constexpr int OZ_THREADS = 192;
+constexpr size_t OZ_SMEM = (size_t)OZ_STAGES * OZ_STAGE_BYTES + 4 * 32 * 17 * 8 + 4 * 128 * 8 + 64 + 1024;
+
+__device__ __forceinline__ uint64_t oz_desc(uint32_t smem_addr) {
+    // SMEM matrix descriptor, no swizzle, K-major: LBO = 128 B (core matrices along K), SBO = 256 B (8-row groups)
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(128 >> 4) << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;                   // descriptor version for sm_100
+    return d;
+}
+__device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void oz_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a mis-programmed pipeline must not hang the GPU box
+__device__ __forceinline__ bool oz_wait(uint64_t* bar, uint32_t parity, int* fail) {
+    for (long spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1L << 24)) { *fail = 1; return false; }
+    return true;
+}
+
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, const int8_t* __restrict__ kq,
+            int n_pad, double kappa, double kdiag, double y_std, double* __restrict__ scratch,
+            double* __restrict__ std_out, long k, int ld, int q, int* __restrict__ fail_flag) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* stages = smem;
+    double* red = reinterpret_cast<double*>(smem + (size_t)OZ_STAGES * OZ_STAGE_BYTES);       // [4 warps][32][17]
+    double* colred = red + 4 * 32 * 17;                                                       // [4][128]
+    uint64_t* full = reinterpret_cast<uint64_t*>(colred + 4 * 128);                           // [3]
+    uint64_t* empty = full + OZ_STAGES;                                                       // [3]
+    uint64_t* acc_full = empty + OZ_STAGES;
+    uint64_t* acc_empty = acc_full + 1;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int fail_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_panels = n_pad / 128, nks = n_pad / 32;
+    const int8_t* kt = kq + (size_t)blockIdx.x * nks * OZ_S * OZ_TILE;
+    double* scr = scratch + (size_t)blockIdx.x * 128 * 128;
+
+    if (tid == 0) {
+        for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 4);
+        mbar_fence_init();
+        fail_s = 0;
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 5) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            int fail = 0;
+            long t = 0;
+            for (int panel = 0; panel < n_panels && !fail; ++panel)
+                for (int pass = 0; pass < 2 && !fail; ++pass) {
+                    const uint32_t nsl = pass == 0 ? 4 : 8;                 // slices this pass reads
+                    for (int ks = 0; ks < (panel + 1) * 4; ++ks, ++t) {
+                        const int s = (int)(t % OZ_STAGES);
+                        if (t >= OZ_STAGES && !oz_wait(&empty[s], (uint32_t)(((t / OZ_STAGES) - 1) & 1), &fail)) break;
+                        unsigned char* dst = stages + (size_t)s * OZ_STAGE_BYTES;
+                        mbar_expect_tx(&full[s], 2 * nsl * OZ_TILE);
+                        tma_load_1d(dst, wq + ((size_t)panel * nks + ks) * OZ_S * OZ_TILE, nsl * OZ_TILE, &full[s]);
+                        tma_load_1d(dst + OZ_S * OZ_TILE, kt + (size_t)ks * OZ_S * OZ_TILE, nsl * OZ_TILE, &full[s]);
+                    }
+                }
+            if (fail) fail_s = 1;
+        }
+    } else if (warp == 4) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int fail = 0;
+            // instruction descriptor: S32 accumulate, signed int8 A and B, K-major both, N = 128, M = 128
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+            long t = 0;
+            int round = 0;                                                   // (panel, pass) counter
+            for (int panel = 0; panel < n_panels && !fail; ++panel)
+                for (int pass = 0; pass < 2 && !fail; ++pass, ++round) {
+                    if (round > 0 && !oz_wait(acc_empty, (uint32_t)((round - 1) & 1), &fail)) break;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const int g_lo = pass == 0 ? 2 : 6;
+                    const int nks_p = (panel + 1) * 4;
+                    for (int ks = 0; ks < nks_p; ++ks, ++t) {
+                        const int s = (int)(t % OZ_STAGES);
+                        if (!oz_wait(&full[s], (uint32_t)((t / OZ_STAGES) & 1), &fail)) break;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_base = smem_u32(stages + (size_t)s * OZ_STAGE_BYTES);
+                        const uint32_t b_base = a_base + OZ_S * OZ_TILE;
+#pragma unroll 1
+                        for (int g = g_lo; g < g_lo + 4; ++g) {
+                            const int a_min = g - OZ_S > 1 ? g - OZ_S : 1, a_max = g - 1 < OZ_S ? g - 1 : OZ_S;
+#pragma unroll 1
+                            for (int a = a_min; a <= a_max; ++a) {
+                                const int b = g - a;
+                                oz_mma(tmem_base + (uint32_t)(g - g_lo) * 128, oz_desc(a_base + (a - 1) * OZ_TILE),
+                                       oz_desc(b_base + (b - 1) * OZ_TILE), idesc, (ks > 0 || a > a_min) ? 1u : 0u);
+                            }
+                        }
+                        oz_commit(&empty[s]);                                // stage free once these MMAs retire
+                    }
+                    oz_commit(acc_full);                                     // accumulators of this (panel, pass) complete
+                }
+            if (fail) fail_s = 1;
+        }
+    } else {
+        // ================= epilogue warps 0..3: TMEM lanes 32*warp .. 32*warp+31 = rows of the panel =================
+        int fail = 0;
+        double colsum[8];                                   // lane l < 16 of this warp: columns 16*c + l, c = 0..7
+#pragma unroll
+        for (int c = 0; c < 8; ++c) colsum[c] = 0.0;
+        double* myred = red + warp * 32 * 17;
+        const int row = warp * 32 + lane;
+        int round = 0;
+        for (int panel = 0; panel < n_panels && !fail; ++panel)
+            for (int pass = 0; pass < 2 && !fail; ++pass, ++round) {
+                if (!oz_wait(acc_full, (uint32_t)(round & 1), &fail)) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const double sig = pass == 1 ? wsig[panel * 128 + row] * kappa : 0.0;
+#pragma unroll 1
+                for (int c = 0; c < 8; ++c) {               // 16 columns at a time
+                    uint32_t d[4][16];
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 128 + c * 16);
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                     : "=r"(d[g][0]), "=r"(d[g][1]), "=r"(d[g][2]), "=r"(d[g][3]), "=r"(d[g][4]),
+                                       "=r"(d[g][5]), "=r"(d[g][6]), "=r"(d[g][7]), "=r"(d[g][8]), "=r"(d[g][9]),
+                                       "=r"(d[g][10]), "=r"(d[g][11]), "=r"(d[g][12]), "=r"(d[g][13]), "=r"(d[g][14]),
+                                       "=r"(d[g][15])
+                                     : "r"(taddr));
+                    }
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        // Horner over the four groups of this pass, weights 2^-7 apart (exact scalings)
+                        double h = (double)(int)d[3][j];
+                        h = fma(h, 0x1p-7, (double)(int)d[2][j]);
+                        h = fma(h, 0x1p-7, (double)(int)d[1][j]);
+                        h = fma(h, 0x1p-7, (double)(int)d[0][j]);
+                        double* sp = scr + (size_t)(c * 16 + j) * 128 + row;
+                        if (pass == 0) {
+                            *sp = h * 0x1p-12;                               // groups 2..5: leading weight 2^-(7*2-2)
+                        } else {
+                            const double v = sig * fma(h, 0x1p-40, *sp);     // groups 6..9: 2^-(7*6-2)
+                            myred[lane * 17 + j] = v * v;
+                        }
+                    }
+                    if (pass == 1) {
+                        __syncwarp();
+                        if (lane < 16) {
+                            double t = 0.0;
+#pragma unroll 8
+                            for (int r = 0; r < 32; ++r) t += myred[r * 17 + lane];
+                            colsum[c] += t;
+                        }
+                        __syncwarp();
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+            }
+        if (fail) fail_s = 1;
+        if (lane < 16) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) colred[warp * 128 + c * 16 + lane] = colsum[c];
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (tid < 128) {
+        const long t = (long)blockIdx.x * 128 + tid;
+        if (t < k) {
+            const double tot = (colred[tid] + colred[128 + tid]) + (colred[256 + tid] + colred[384 + tid]);
+            double var = __dadd_rn(kdiag, -tot);                                       // sklearn:_gpr.py:480-481
+            if (var < 0.0) var = 0.0;                                                  // :485-491
+            std_out[t * ld + q] = sqrt(__dmul_rn(var, __dmul_rn(y_std, y_std)));       // :494,500
+        }
+    }
+    if (tid == 0 && fail_s) *fail_flag = 1;
+}
+
+// ---------------------------------------------------------------- W -> row scales + int8 slices (upload time)
+// src: row-major n_pad-strided lower-triangular W (transposed = 1: src holds W^T).  One warp per row.
+__global__ void k_slice_w(const double* __restrict__ src, int n, int ld, int transposed, int n_pad,
+                          int8_t* __restrict__ wq, double* __restrict__ wsig) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n_pad) return;
+    const int nks = n_pad / 32;
+    double mx = 0.0;
+    if (row < n)
+        for (int j = lane; j <= row; j += 32) {
+            const double w = transposed ? src[(size_t)j * ld + row] : src[(size_t)row * ld + j];
+            mx = fmax(mx, fabs(w));
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    int e = 0;
+    double sig = 1.0;
+    if (mx > 0.0) { frexp(mx, &e); sig = ldexp(1.0, e); }    // mx = f * 2^e with f in [0.5, 1)  ->  |w| / sig < 1
+    if (lane == 0) wsig[row] = sig;
+    const double inv = 1.0 / sig;                           // power of two: exact
+    const int panel = row >> 7, r = row & 127;
+    for (int j = lane; j < n_pad; j += 32) {
+        double w = 0.0;
+        if (row < n && j <= row) w = (transposed ? src[(size_t)j * ld + row] : src[(size_t)row * ld + j]) * inv;
+        const int ks = j >> 5, b = j & 31;
+        int8_t* base = wq + ((size_t)panel * nks + ks) * OZ_S * OZ_TILE + (r >> 3) * 256 + (b >> 4) * 128 + (r & 7) * 16 + (b & 15);
+        double y = w * 64.0;
+#pragma unroll
+        for (int a = 0; a < OZ_S; ++a) {
+            const double qd = rint(y);
+            base[(size_t)a * OZ_TILE] = (int8_t)(int)qd;
+            y = (y - qd) * 128.0;                           // exact: |y - qd| <= 1/2
+        }
+    }
+}
+
+int launch_slice_w(const double* src, int n, int ld, int transposed, int8_t* wq, double* wsig, cudaStream_t st) {
+    const int n_pad = padded_n(n);
+    ProfScope prof(PROF_OTHER, st);
+    k_slice_w<<<(n_pad + 7) / 8, 256, 0, st>>>(src, n, ld, transposed, n_pad, wq, wsig);
+    BK_LAUNCH_CHECK("k_slice_w");
+    return 0;
+}
+
+int launch_var_ozaki(const bk_gp_s* h, int q, const int8_t* kq, double kappa, long k, double* std_out,
+                     double* scratch, int* fail_flag, cudaStream_t st) {
+    const GpOutput& o = h->out[q];
+    if (!o.wq || !o.wsig) return set_error("int8 variance path requested but output %d has no sliced L^-1", q);
+    static bool attr_set = false;
+    if (!attr_set) {
+        BK_CUDA(cudaFuncSetAttribute(k_var_ozaki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+        attr_set = true;
+    }
+    const unsigned grid = (unsigned)((k + 127) / 128);
+    ProfScope prof(PROF_VAR, st);
+    k_var_ozaki<<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std, scratch, std_out,
+                                                   k, h->m, q, fail_flag);
+    BK_LAUNCH_CHECK("k_var_ozaki");
+    return 0;
+}
+
+}  // namespace bk

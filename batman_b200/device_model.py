@@ -10,6 +10,7 @@ output q (DESIGN.md §"Data layout"):
                 (built lazily: only sigma needs it)
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -48,7 +49,10 @@ class DeviceModel:
         with torch.cuda.device(self.device):
             Xd = torch.from_numpy(X).to(self.device)
             self.xs, self.alpha = [], []
-            self.wt = list(wts) if wts is not None else [None] * self.m
+            # wts[q] = (FP64 tiles, int8 slices, row scales) of L^-1 when the fit already produced them
+            self.wt = [w[0] if w is not None else None for w in wts] if wts is not None else [None] * self.m
+            self.wq = [w[1] if w is not None else None for w in wts] if wts is not None else [None] * self.m
+            self.wsig = [w[2] if w is not None else None for w in wts] if wts is not None else [None] * self.m
             for q, spec in enumerate(specs):
                 ls = torch.from_numpy(np.asarray(spec.ls, dtype=np.float64)).to(self.device)
                 xs = torch.zeros((self.n_pad, self.P), dtype=torch.float64, device=self.device)
@@ -60,6 +64,15 @@ class DeviceModel:
                 self._set_output(q)
         self._workspace = None
         self._scaler = None
+        self.sigma_kernel = 'dmma'
+        self.set_sigma_kernel(os.environ.get('BATMAN_B200_SIGMA', 'dmma'))
+
+    def set_sigma_kernel(self, name):
+        """'dmma' = FP64 tensor cores (k_var_trmm); 'int8' = tcgen05 int8 + TMEM, error-free slicing (k_var_ozaki)."""
+        if name not in ('dmma', 'int8'):
+            raise ValueError("sigma kernel must be 'dmma' or 'int8'")
+        _lib.check(self.lib.bk_gp_set_var_mode(self.handle, 1 if name == 'int8' else 0))
+        self.sigma_kernel = name
 
     # -- C handle ------------------------------------------------------------------------------
     def _set_output(self, q):
@@ -67,6 +80,7 @@ class DeviceModel:
         _lib.check(self.lib.bk_gp_set_output(
             self.handle, q, spec.kind, spec.c0, spec.c1, spec.kdiag, _lib.as_double_array(spec.ls),
             _ptr(self.xs[q]), _ptr(self.alpha[q]), _ptr(self.wt[q]), self.y_means[q], self.y_stds[q]))
+        _lib.check(self.lib.bk_gp_set_output_int8(self.handle, q, _ptr(self.wq[q]), _ptr(self.wsig[q])))
 
     def set_scaler(self, scale, mn):
         """MinMaxScaler fused into the kernels (surrogate_model.py:181); None = identity."""
@@ -86,7 +100,7 @@ class DeviceModel:
         from .lml import inverse_tiles
         for q in range(self.m):
             if self.wt[q] is None:
-                self.wt[q] = inverse_tiles(self._Ls[q], self.device)
+                self.wt[q], self.wq[q], self.wsig[q] = inverse_tiles(self._Ls[q], self.device)
                 self._set_output(q)
 
     def close(self):
@@ -121,8 +135,12 @@ class DeviceModel:
             self.ensure_w()
         ws, ws_bytes = self.workspace(k, return_std)
         with torch.cuda.device(self.device):
+            if return_std and self.sigma_kernel == 'int8':
+                ws[-32:].zero_()                      # pipeline-timeout flag of k_var_ozaki lives in the tail
             _lib.check(self.lib.bk_gp_predict(self.handle, _ptr(pts_dev), k, _ptr(mean), _ptr(std), _ptr(ws),
                                               ws_bytes, current_stream_ptr()))
+            if return_std and self.sigma_kernel == 'int8' and float(ws[-32:].abs().sum().item()) != 0.0:
+                raise _lib.BatmanB200Error("k_var_ozaki: an mbarrier wait timed out (pipeline fault)")
         return mean, std
 
     E2E_CHUNK = 8 * 148 * 128 * 8        # rows per pipelined slice (8 K* chunks)

@@ -64,7 +64,8 @@ def lml_batched(X_dev, y_dev, specs):
 def factorise(X_dev, y_dev, spec):
     """Final state at the chosen theta (sklearn:_gpr.py:349-367).
 
-    -> (L (n, n) numpy lower, alpha (n,) numpy, lml float, packed L^-1 tiles as a CUDA tensor)."""
+    -> (L (n, n) numpy lower, alpha (n,) numpy, lml float, (FP64 tiles, int8 slices, row scales) of L^-1 as
+    CUDA tensors)."""
     lib = _lib.load()
     X_dev, y_dev = X_dev.contiguous(), y_dev.contiguous()
     n, p = X_dev.shape
@@ -75,27 +76,32 @@ def factorise(X_dev, y_dev, spec):
         L = torch.empty((n_pad, n_pad), dtype=torch.float64, device=dev)
         alpha = torch.empty(n_pad, dtype=torch.float64, device=dev)
         wt = torch.empty(lib.bk_gp_wtiles_len(n), dtype=torch.float64, device=dev)
+        wq = torch.empty(lib.bk_gp_wq_bytes(n), dtype=torch.int8, device=dev)
+        wsig = torch.empty(n_pad, dtype=torch.float64, device=dev)
         lml = torch.empty(1, dtype=torch.float64, device=dev)
         info = torch.zeros(1, dtype=torch.int32, device=dev)
         _lib.check(lib.bk_gp_factorise(_ptr(X_dev), _ptr(y_dev), n, p, spec.kind, spec.c0, spec.c1, spec.kdiag,
-                                       _lib.as_double_array(spec.ls), _ptr(L), _ptr(alpha), _ptr(wt), _ptr(lml),
-                                       _ptr(info), _ptr(ws), ws.numel(), _stream()))
+                                       _lib.as_double_array(spec.ls), _ptr(L), _ptr(alpha), _ptr(wt), _ptr(wq),
+                                       _ptr(wsig), _ptr(lml), _ptr(info), _ptr(ws), ws.numel(), _stream()))
         if int(info.item()) != 0:
             raise np.linalg.LinAlgError(
                 "The kernel is not returning a positive definite matrix. Try gradually increasing the "
                 "'alpha' parameter of your GaussianProcessRegressor estimator.")   # sklearn:_gpr.py:354-360
         L_host = np.tril(L[:n, :n].cpu().numpy())
-        return L_host, alpha[:n].cpu().numpy(), float(lml.item()), wt
+        return L_host, alpha[:n].cpu().numpy(), float(lml.item()), (wt, wq, wsig)
 
 
 def inverse_tiles(L_host, device):
-    """Packed L^-1 tiles from a given Cholesky factor (models adopted from scikit-learn state)."""
+    """L^-1 from a given Cholesky factor (models adopted from scikit-learn state): FP64 DMMA tiles, int8 slices
+    and their row scales."""
     lib = _lib.load()
     n = L_host.shape[0]
     with torch.cuda.device(device):
         L = torch.from_numpy(np.ascontiguousarray(L_host, dtype=np.float64)).to(device)
         ws = _workspace(device, lib.bk_lml_workspace(n, 1, 1))
         wt = torch.empty(lib.bk_gp_wtiles_len(n), dtype=torch.float64, device=device)
-        _lib.check(lib.bk_tri_inverse_pack(_ptr(L), n, _ptr(wt), _ptr(ws), ws.numel(), _stream()))
+        wq = torch.empty(lib.bk_gp_wq_bytes(n), dtype=torch.int8, device=device)
+        wsig = torch.empty(lib.bk_gp_padded_n(n), dtype=torch.float64, device=device)
+        _lib.check(lib.bk_tri_inverse_pack(_ptr(L), n, _ptr(wt), _ptr(wq), _ptr(wsig), _ptr(ws), ws.numel(), _stream()))
         torch.cuda.current_stream().synchronize()
-    return wt
+    return wt, wq, wsig

@@ -148,22 +148,37 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(const PredictParams<P>
                 const int jg = tile * PRED_TJ + j8;
 #pragma unroll
                 for (int e = 0; e < PRED_TP; ++e) {
-                    unsigned long long pk[8];
+                    unsigned int pk[8][2];
 #pragma unroll
-                    for (int a = 0; a < 8; ++a) pk[a] = 0ull;
+                    for (int a = 0; a < 8; ++a) pk[a][0] = pk[a][1] = 0u;
 #pragma unroll
                     for (int jj = 0; jj < 8; ++jj) {
-                        double y = __dmul_rn(__dmul_rn(kbuf[e][jj], prm.inv_kappa), 64.0);
+                        // X = rint(k/kappa * 2^55) = hi * 2^28 + lo from two magic-number roundings (no F2I), then
+                        // signed base-128 digits in [-64, 63] with 32-bit integer ops: X = sum_a q_a 2^(56-7a)
+                        const double x27 = __dmul_rn(__dmul_rn(kbuf[e][jj], prm.inv_kappa), 0x1p27);
+                        const double hm = __dadd_rn(x27, 6755399441055744.0);
+                        int hi = __double2loint(hm);                                  // rint(x * 2^27), |hi| <= 2^27
+                        const double r28 = __dmul_rn(__dadd_rn(x27, -__dadd_rn(hm, -6755399441055744.0)), 0x1p28);
+                        int lo = __double2loint(__dadd_rn(r28, 6755399441055744.0));  // |lo| <= 2^27
+                        const int sh = 8 * (jj & 3), w = jj >> 2;
 #pragma unroll
-                        for (int a = 0; a < 8; ++a) {
-                            const double qd = rint(y);
-                            pk[a] |= (unsigned long long)(unsigned char)(signed char)__double2int_rn(qd) << (8 * jj);
-                            y = __dmul_rn(__dadd_rn(y, -qd), 128.0);
+                        for (int a = 7; a >= 4; --a) {                                // slices 8..5 from lo
+                            const int dgt = ((lo + 64) & 127) - 64;
+                            pk[a][w] |= (unsigned int)(dgt & 255) << sh;
+                            lo = (lo - dgt) >> 7;
                         }
+                        hi += lo;                                                     // carry out of the low half
+#pragma unroll
+                        for (int a = 3; a >= 1; --a) {                                // slices 4..2 from hi
+                            const int dgt = ((hi + 64) & 127) - 64;
+                            pk[a][w] |= (unsigned int)(dgt & 255) << sh;
+                            hi = (hi - dgt) >> 7;
+                        }
+                        pk[0][w] |= (unsigned int)(hi & 255) << sh;                   // slice 1: |hi| <= 64
                     }
                     int8_t* d = qdst[e] + (size_t)(jg >> 5) * 8 * 4096 + ((jg & 31) >> 4) * 128 + (jg & 15);
 #pragma unroll
-                    for (int a = 0; a < 8; ++a) *reinterpret_cast<unsigned long long*>(d + (size_t)a * 4096) = pk[a];
+                    for (int a = 0; a < 8; ++a) *reinterpret_cast<uint2*>(d + (size_t)a * 4096) = make_uint2(pk[a][0], pk[a][1]);
                 }
             }
             if constexpr (WRITE_K == 1) {

@@ -11,11 +11,14 @@
 // 128x128 int32 accumulator groups fit in TMEM (512 columns): pass 0 = groups 2..5 (slices 1..4, 10 MMAs per
 // 32-wide k slab), pass 1 = groups 6..9 (slices 1..8, 26 MMAs).  The pass-0 combination is parked in an
 // L2-resident scratch tile and added in pass 1.
-//   warp 5 lane 0 : TMA producer  (cp.async.bulk of pre-packed slice tiles, 3-stage full/empty mbarrier ring)
+//   warp 5 lane 0 : TMA producer  (cp.async.bulk of pre-packed slice tiles, 6-slot full/empty mbarrier ring)
 //   warp 4 lane 0 : MMA issuer    (tcgen05.mma.cta_group::1.kind::i8, M128 N128 K32, SMEM descriptors, commit)
-//   warps 0..3    : epilogue      (tcgen05.ld -> int32 -> FP64 Horner -> v^2 -> column sums)
+//   warps 0..3    : epilogue      (tcgen05.ld -> exact int64 combine -> FP64 -> sum of v^2; one thread per test
+//                                  point: TMEM lanes = test points (M side = K* slices), columns = W rows (N side))
 // Operand tiles are packed on the producer side (W at upload, K* by K1) in the non-swizzled K-major UMMA
 // layout: element (row r, byte b) of a 128 x 32 B tile at (r/8)*256 + (b/16)*128 + (r%8)*16 + b%16.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "model.h"
 
@@ -23,10 +26,11 @@ namespace bk {
 
 constexpr int OZ_S = 8;                       // int8 slices per operand
 constexpr int OZ_TILE = 4096;                 // bytes of one 128 x 32 B slice tile
-constexpr int OZ_STAGES = 3;
-constexpr int OZ_STAGE_BYTES = 2 * OZ_S * OZ_TILE;         // A slices at +0, B slices at +32 KiB
+constexpr int OZ_SLOTS = 6;                   // ring of 32 KiB slots (8 slice tiles each)
+constexpr int OZ_SLOT_BYTES = OZ_S * OZ_TILE; // pass 0: one slot per k slab = [A slices 1..4 | B slices 1..4]
+                                              // pass 1: two slots per k slab = [A slices 1..8], [B slices 1..8]
 constexpr int OZ_THREADS = 192;
-constexpr size_t OZ_SMEM = (size_t)OZ_STAGES * OZ_STAGE_BYTES + 4 * 32 * 17 * 8 + 4 * 128 * 8 + 64 + 1024;
+constexpr size_t OZ_SMEM = (size_t)OZ_SLOTS * OZ_SLOT_BYTES + 4 * 32 * 17 * 8 + 4 * 128 * 8 + 2 * OZ_SLOTS * 8 + 64 + 1024;
 
 __device__ __forceinline__ uint64_t oz_desc(uint32_t smem_addr) {
     // SMEM matrix descriptor, no swizzle, K-major: LBO = 128 B (core matrices along K), SBO = 256 B (8-row groups)
@@ -53,17 +57,39 @@ __device__ __forceinline__ bool oz_wait(uint64_t* bar, uint32_t parity, int* fai
     return true;
 }
 
+// All slice pairs (a, b), a + b = g, of the four accumulator groups of one pass for one k slab, fully unrolled:
+// per MMA the issuing thread only adds a tile offset to two pre-built descriptors (start-address field, 16-B units).
+// M side (TMEM lanes) = the 128 test points (K* slices), N side (TMEM columns) = the 128 rows of the W panel.
+template <int PASS>
+__device__ __forceinline__ void oz_issue_slab(uint32_t tmem_base, uint64_t kdesc0, uint64_t wdesc0, uint32_t idesc,
+                                              uint32_t not_first) {
+    constexpr int G_LO = PASS == 0 ? 2 : 6;
+#pragma unroll
+    for (int g = G_LO; g < G_LO + 4; ++g) {
+        constexpr int S = OZ_S;
+#pragma unroll
+        for (int a = 1; a <= S; ++a) {
+            const int b = g - a;                       // a = W slice, b = K* slice
+            if (b >= 1 && b <= S) {
+                const bool first_of_group = (a == (g - S > 1 ? g - S : 1));
+                oz_mma(tmem_base + (uint32_t)(g - G_LO) * 128, kdesc0 + (uint64_t)((b - 1) * (OZ_TILE >> 4)),
+                       wdesc0 + (uint64_t)((a - 1) * (OZ_TILE >> 4)), idesc, first_of_group ? not_first : 1u);
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, const int8_t* __restrict__ kq,
             int n_pad, double kappa, double kdiag, double y_std, double* __restrict__ scratch,
-            double* __restrict__ std_out, long k, int ld, int q, int* __restrict__ fail_flag) {
+            double* __restrict__ std_out, long k, int ld, int q, int* __restrict__ fail_flag, int dbg) {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stages = smem;
-    double* red = reinterpret_cast<double*>(smem + (size_t)OZ_STAGES * OZ_STAGE_BYTES);       // [4 warps][32][17]
+    double* red = reinterpret_cast<double*>(smem + (size_t)OZ_SLOTS * OZ_SLOT_BYTES);         // [4 warps][32][17]
     double* colred = red + 4 * 32 * 17;                                                       // [4][128]
-    uint64_t* full = reinterpret_cast<uint64_t*>(colred + 4 * 128);                           // [3]
-    uint64_t* empty = full + OZ_STAGES;                                                       // [3]
-    uint64_t* acc_full = empty + OZ_STAGES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(colred + 4 * 128);                           // [slots]
+    uint64_t* empty = full + OZ_SLOTS;                                                        // [slots]
+    uint64_t* acc_full = empty + OZ_SLOTS;
     uint64_t* acc_empty = acc_full + 1;
     __shared__ uint32_t tmem_base_s;
     __shared__ int fail_s;
@@ -74,7 +100,7 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
     double* scr = scratch + (size_t)blockIdx.x * 128 * 128;
 
     if (tid == 0) {
-        for (int s = 0; s < OZ_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < OZ_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, 4);
         mbar_fence_init();
@@ -93,19 +119,29 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
         // ================= TMA producer =================
         if (lane == 0) {
             int fail = 0;
-            long t = 0;
+            long u = 0;                                                      // running slot-use counter
+            auto fill = [&](const int8_t* a_src, uint32_t a_bytes, const int8_t* b_src, uint32_t b_bytes) -> bool {
+                const int s = (int)(u % OZ_SLOTS);
+                if (u >= OZ_SLOTS && !oz_wait(&empty[s], (uint32_t)(((u / OZ_SLOTS) - 1) & 1), &fail)) return false;
+                unsigned char* dst = stages + (size_t)s * OZ_SLOT_BYTES;
+                if (dbg & 2) { a_bytes = 16; b_bytes = 0; }                 // timing experiment: no operand traffic
+                mbar_expect_tx(&full[s], a_bytes + b_bytes);
+                tma_load_1d(dst, a_src, a_bytes, &full[s]);
+                if (b_bytes) tma_load_1d(dst + a_bytes, b_src, b_bytes, &full[s]);
+                ++u;
+                return true;
+            };
             for (int panel = 0; panel < n_panels && !fail; ++panel)
-                for (int pass = 0; pass < 2 && !fail; ++pass) {
-                    const uint32_t nsl = pass == 0 ? 4 : 8;                 // slices this pass reads
-                    for (int ks = 0; ks < (panel + 1) * 4; ++ks, ++t) {
-                        const int s = (int)(t % OZ_STAGES);
-                        if (t >= OZ_STAGES && !oz_wait(&empty[s], (uint32_t)(((t / OZ_STAGES) - 1) & 1), &fail)) break;
-                        unsigned char* dst = stages + (size_t)s * OZ_STAGE_BYTES;
-                        mbar_expect_tx(&full[s], 2 * nsl * OZ_TILE);
-                        tma_load_1d(dst, wq + ((size_t)panel * nks + ks) * OZ_S * OZ_TILE, nsl * OZ_TILE, &full[s]);
-                        tma_load_1d(dst + OZ_S * OZ_TILE, kt + (size_t)ks * OZ_S * OZ_TILE, nsl * OZ_TILE, &full[s]);
+                for (int pass = 0; pass < 2 && !fail; ++pass)
+                    for (int ks = 0; ks < (panel + 1) * 4 && !fail; ++ks) {
+                        const int8_t* a_src = wq + ((size_t)panel * nks + ks) * OZ_S * OZ_TILE;
+                        const int8_t* b_src = kt + (size_t)ks * OZ_S * OZ_TILE;
+                        if (pass == 0) {
+                            fill(a_src, 4 * OZ_TILE, b_src, 4 * OZ_TILE);
+                        } else {
+                            if (fill(a_src, OZ_S * OZ_TILE, nullptr, 0)) fill(b_src, OZ_S * OZ_TILE, nullptr, 0);
+                        }
                     }
-                }
             if (fail) fail_s = 1;
         }
     } else if (warp == 4) {
@@ -114,7 +150,7 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
             int fail = 0;
             // instruction descriptor: S32 accumulate, signed int8 A and B, K-major both, N = 128, M = 128
             const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-            long t = 0;
+            long u = 0;
             int round = 0;                                                   // (panel, pass) counter
             for (int panel = 0; panel < n_panels && !fail; ++panel)
                 for (int pass = 0; pass < 2 && !fail; ++pass, ++round) {
@@ -122,44 +158,45 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const int g_lo = pass == 0 ? 2 : 6;
                     const int nks_p = (panel + 1) * 4;
-                    for (int ks = 0; ks < nks_p; ++ks, ++t) {
-                        const int s = (int)(t % OZ_STAGES);
-                        if (!oz_wait(&full[s], (uint32_t)((t / OZ_STAGES) & 1), &fail)) break;
+                    for (int ks = 0; ks < nks_p; ++ks) {
+                        const int s0 = (int)(u % OZ_SLOTS), s1 = (int)((u + 1) % OZ_SLOTS);
+                        if (!oz_wait(&full[s0], (uint32_t)((u / OZ_SLOTS) & 1), &fail)) break;
+                        if (pass == 1 && !oz_wait(&full[s1], (uint32_t)(((u + 1) / OZ_SLOTS) & 1), &fail)) break;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t a_base = smem_u32(stages + (size_t)s * OZ_STAGE_BYTES);
-                        const uint32_t b_base = a_base + OZ_S * OZ_TILE;
-#pragma unroll 1
-                        for (int g = g_lo; g < g_lo + 4; ++g) {
-                            const int a_min = g - OZ_S > 1 ? g - OZ_S : 1, a_max = g - 1 < OZ_S ? g - 1 : OZ_S;
-#pragma unroll 1
-                            for (int a = a_min; a <= a_max; ++a) {
-                                const int b = g - a;
-                                oz_mma(tmem_base + (uint32_t)(g - g_lo) * 128, oz_desc(a_base + (a - 1) * OZ_TILE),
-                                       oz_desc(b_base + (b - 1) * OZ_TILE), idesc, (ks > 0 || a > a_min) ? 1u : 0u);
-                            }
-                        }
-                        oz_commit(&empty[s]);                                // stage free once these MMAs retire
+                        const uint32_t w_base = smem_u32(stages + (size_t)s0 * OZ_SLOT_BYTES);
+                        const uint32_t k_base = pass == 0 ? w_base + 4 * OZ_TILE : smem_u32(stages + (size_t)s1 * OZ_SLOT_BYTES);
+                        if (pass == 0) oz_issue_slab<0>(tmem_base, oz_desc(k_base), oz_desc(w_base), idesc, ks > 0 ? 1u : 0u);
+                        else oz_issue_slab<1>(tmem_base, oz_desc(k_base), oz_desc(w_base), idesc, ks > 0 ? 1u : 0u);
+                        oz_commit(&empty[s0]);                               // slot(s) free once these MMAs retire
+                        if (pass == 1) oz_commit(&empty[s1]);
+                        u += pass == 0 ? 1 : 2;
                     }
                     oz_commit(acc_full);                                     // accumulators of this (panel, pass) complete
                 }
             if (fail) fail_s = 1;
         }
     } else {
-        // ================= epilogue warps 0..3: TMEM lanes 32*warp .. 32*warp+31 = rows of the panel =================
+        // ================= epilogue warps 0..3: TMEM lane 32*warp + lane = test point, columns = rows of the W panel ====
         int fail = 0;
-        double colsum[8];                                   // lane l < 16 of this warp: columns 16*c + l, c = 0..7
-#pragma unroll
-        for (int c = 0; c < 8; ++c) colsum[c] = 0.0;
-        double* myred = red + warp * 32 * 17;
-        const int row = warp * 32 + lane;
+        double vsum = 0.0;                                  // sum_i v_i^2 of this thread's test point
+        const int tp = warp * 32 + lane;
+        double* sigs = red;                                 // [128] sigma_i * kappa of the current panel
         int round = 0;
         for (int panel = 0; panel < n_panels && !fail; ++panel)
             for (int pass = 0; pass < 2 && !fail; ++pass, ++round) {
+                if (pass == 1) {
+                    // named barrier among the 4 epilogue warps: previous panel's sigs fully consumed, then refill
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    sigs[tp] = wsig[panel * 128 + tp] * kappa;
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
                 if (!oz_wait(acc_full, (uint32_t)(round & 1), &fail)) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const double sig = pass == 1 ? wsig[panel * 128 + row] * kappa : 0.0;
 #pragma unroll 1
-                for (int c = 0; c < 8; ++c) {               // 16 columns at a time
+                for (int c = 0; c < ((dbg & 1) ? 0 : 8); ++c) {   // 16 W rows at a time (dbg bit 0: timing experiment, no drain)
+                    double sv[16];                          // pass-0 partials of this chunk: loads fly under the TMEM read
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sv[j] = pass == 1 ? scr[(size_t)(c * 16 + j) * 128 + tp] : 0.0;
                     uint32_t d[4][16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
@@ -175,28 +212,17 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        // Horner over the four groups of this pass, weights 2^-7 apart (exact scalings)
-                        double h = (double)(int)d[3][j];
-                        h = fma(h, 0x1p-7, (double)(int)d[2][j]);
-                        h = fma(h, 0x1p-7, (double)(int)d[1][j]);
-                        h = fma(h, 0x1p-7, (double)(int)d[0][j]);
-                        double* sp = scr + (size_t)(c * 16 + j) * 128 + row;
+                        // Combine the four groups of the pass EXACTLY in int64 (weights 2^-7 apart; |D_g| < 2^29 so
+                        // |h| < 2^51), then one integer add + one DADD converts to FP64 (I2F.F64 is slow).
+                        const long long h64 = ((long long)(int)d[0][j] << 21) + ((long long)(int)d[1][j] << 14) +
+                                              ((long long)(int)d[2][j] << 7) + (long long)(int)d[3][j];
+                        const double h = __longlong_as_double(h64 + 0x4338000000000000ll) - 6755399441055744.0;
                         if (pass == 0) {
-                            *sp = h * 0x1p-12;                               // groups 2..5: leading weight 2^-(7*2-2)
+                            scr[(size_t)(c * 16 + j) * 128 + tp] = h * 0x1p-33;          // groups 2..5: 2^-12 * 2^-21
                         } else {
-                            const double v = sig * fma(h, 0x1p-40, *sp);     // groups 6..9: 2^-(7*6-2)
-                            myred[lane * 17 + j] = v * v;
+                            const double v = sigs[c * 16 + j] * fma(h, 0x1p-61, sv[j]);  // groups 6..9: 2^-40 * 2^-21
+                            vsum = fma(v, v, vsum);
                         }
-                    }
-                    if (pass == 1) {
-                        __syncwarp();
-                        if (lane < 16) {
-                            double t = 0.0;
-#pragma unroll 8
-                            for (int r = 0; r < 32; ++r) t += myred[r * 17 + lane];
-                            colsum[c] += t;
-                        }
-                        __syncwarp();
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -204,10 +230,7 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
                 if (lane == 0) mbar_arrive(acc_empty);
             }
         if (fail) fail_s = 1;
-        if (lane < 16) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) colred[warp * 128 + c * 16 + lane] = colsum[c];
-        }
+        colred[tp] = vsum;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -215,8 +238,7 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
     if (tid < 128) {
         const long t = (long)blockIdx.x * 128 + tid;
         if (t < k) {
-            const double tot = (colred[tid] + colred[128 + tid]) + (colred[256 + tid] + colred[384 + tid]);
-            double var = __dadd_rn(kdiag, -tot);                                       // sklearn:_gpr.py:480-481
+            double var = __dadd_rn(kdiag, -colred[tid]);                                       // sklearn:_gpr.py:480-481
             if (var < 0.0) var = 0.0;                                                  // :485-491
             std_out[t * ld + q] = sqrt(__dmul_rn(var, __dmul_rn(y_std, y_std)));       // :494,500
         }
@@ -279,8 +301,9 @@ int launch_var_ozaki(const bk_gp_s* h, int q, const int8_t* kq, double kappa, lo
     }
     const unsigned grid = (unsigned)((k + 127) / 128);
     ProfScope prof(PROF_VAR, st);
+    static int dbg = getenv("BK_OZ_DBG") ? atoi(getenv("BK_OZ_DBG")) : 0;
     k_var_ozaki<<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std, scratch, std_out,
-                                                   k, h->m, q, fail_flag);
+                                                   k, h->m, q, fail_flag, dbg);
     BK_LAUNCH_CHECK("k_var_ozaki");
     return 0;
 }

@@ -192,10 +192,10 @@ def test_int8_tensor_core_sigma_matches_fp64_path(n, p, kind, ls):
     k = kriging_from_states([st])
     rng = np.random.RandomState(5)
     pts = np.vstack([rng.rand(700, p), st['X_train'][:5]])
+    k._model().set_sigma_kernel('dmma')
     m0, s0 = k.evaluate(pts)
     k._model().set_sigma_kernel('int8')
     m1, s1 = k.evaluate(pts)
-    k._model().set_sigma_kernel('dmma')
     prior = ogp.kernel_diag(st['tree']) * st['y_std'] ** 2
     np.testing.assert_array_equal(m0, m1)
     err = np.max(np.abs(s1 ** 2 - s0 ** 2)) / prior

@@ -123,9 +123,18 @@ class DeviceModel:
             return None, 0
         if self._workspace is None or self._workspace.numel() * 8 < need:
             self._workspace = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
+            self._workspace[-32:].zero_()             # pipeline-fault flag of k_var_ozaki lives in the tail
         return self._workspace, self._workspace.numel() * 8
 
-    def predict_device(self, pts_dev, return_std=True):
+    def check_pipeline_flag(self):
+        """k_var_ozaki records an mbarrier time-out (a pipeline fault) in the tail of the workspace instead of
+        hanging the GPU; reading it synchronises, so the pipelined host path checks once per call."""
+        ws = self._workspace
+        if ws is not None and self.sigma_kernel == 'int8' and float(ws[-32:].abs().sum().item()) != 0.0:
+            ws[-32:].zero_()
+            raise _lib.BatmanB200Error("k_var_ozaki: an mbarrier wait timed out (pipeline fault)")
+
+    def predict_device(self, pts_dev, return_std=True, check=True):
         """pts_dev: (k, p) float64 CUDA tensor -> (mean, std) CUDA tensors (k, m); std None if not requested."""
         pts_dev = pts_dev.contiguous()          # the C ABI takes dense row-major buffers
         k = pts_dev.shape[0]
@@ -137,12 +146,10 @@ class DeviceModel:
             self.ensure_w()
         ws, ws_bytes = self.workspace(k, return_std)
         with torch.cuda.device(self.device):
-            if return_std and self.sigma_kernel == 'int8':
-                ws[-32:].zero_()                      # pipeline-timeout flag of k_var_ozaki lives in the tail
             _lib.check(self.lib.bk_gp_predict(self.handle, _ptr(pts_dev), k, _ptr(mean), _ptr(std), _ptr(ws),
                                               ws_bytes, current_stream_ptr()))
-            if return_std and self.sigma_kernel == 'int8' and float(ws[-32:].abs().sum().item()) != 0.0:
-                raise _lib.BatmanB200Error("k_var_ozaki: an mbarrier wait timed out (pipeline fault)")
+            if return_std and check:
+                self.check_pipeline_flag()
         return mean, std
 
     E2E_CHUNK = 8 * 148 * 128 * 8        # rows per pipelined slice (8 K* chunks)
@@ -176,7 +183,7 @@ class DeviceModel:
                         ev_in.record(s_in)
                     s_main.wait_event(ev_in)
                     pts.record_stream(s_main)
-                    mean, std = self.predict_device(pts, return_std)
+                    mean, std = self.predict_device(pts, return_std, check=False)
                     ev = torch.cuda.Event()
                     ev.record(s_main)
                     nxt = (lo, hi, mean, std, ev)
@@ -193,4 +200,6 @@ class DeviceModel:
                             torch.from_numpy(out_std[plo:phi]).copy_(pstd)
                 pending = nxt
             s_main.synchronize()
+            if return_std:
+                self.check_pipeline_flag()
         return out_mean, out_std

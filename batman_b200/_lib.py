@@ -39,9 +39,9 @@ SIGNATURES = {
     'bk_lml_batched': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, c_double_p, c_double_p,
                                       c_double_p, c_double_p, vp, vp, ctypes.c_size_t, vp]),
     'bk_gp_factorise': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
-                                       ctypes.c_double, ctypes.c_double, c_double_p, vp, vp, vp, vp, vp, vp, vp, vp,
-                                       ctypes.c_size_t, vp]),
-    'bk_tri_inverse_pack': (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_size_t, vp]),
+                                       ctypes.c_double, ctypes.c_double, c_double_p, vp, vp, vp, vp, vp, ctypes.c_int,
+                                       vp, vp, vp, ctypes.c_size_t, vp]),
+    'bk_tri_inverse_pack': (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, ctypes.c_size_t, vp]),
     'bk_sobol_nsums': (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     'bk_sobol_nslots': (ctypes.c_int, []),
     'bk_design_rows': (ctypes.c_int, [ctypes.c_uint64, ctypes.c_long, ctypes.c_long, ctypes.c_int, c_int_p,

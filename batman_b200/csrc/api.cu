@@ -41,8 +41,8 @@ ProfScope::~ProfScope() {
 
 // kernels (other translation units)
 int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar, int8_t* kq,
-                   double kappa, cudaStream_t st);
-int launch_var_ozaki(const bk_gp_s* h, int q, const int8_t* kq, double kappa, long k, double* std_out,
+                   int kq_scheme, double kappa, cudaStream_t st);
+int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, double kappa, long k, double* std_out,
                      double* scratch, int* fail_flag, cudaStream_t st);
 int launch_var(const bk_gp_s* h, int q, const double* kstar, long k, double* std_out, cudaStream_t st);
 int launch_pack_w(const double* w, int n, double* out, cudaStream_t st);
@@ -67,9 +67,10 @@ int lml_batched(const double* X, const double* y, int n, int p, int R, const int
                 cudaStream_t st);
 int gp_factorise(const double* X, const double* y, int n, int p, int kind, double c0, double c1, double kdiag,
                  const double* ls, double* L_out, double* alpha_out, double* wt_tiles_out, int8_t* wq_out,
-                 double* wsig_out, double* lml_out, int* info_out, void* ws, size_t ws_bytes, cudaStream_t st);
-int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, int8_t* wq_out, double* wsig_out, void* ws,
-                     size_t ws_bytes, cudaStream_t st);
+                 double* wsig_out, int wq_scheme, double* lml_out, int* info_out, void* ws, size_t ws_bytes,
+                 cudaStream_t st);
+int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, int8_t* wq_out, double* wsig_out, int wq_scheme,
+                     void* ws, size_t ws_bytes, cudaStream_t st);
 int sobol_nsums_host(int p, int second);
 int sobol_nslots_host();
 
@@ -200,8 +201,14 @@ int bk_gp_set_output_int8(bk_gp_t h, int q, const int8_t* wq_dev, const double* 
 
 int bk_gp_set_var_mode(bk_gp_t h, int mode) {
     if (!h) return set_error("bk_gp_set_var_mode: NULL handle");
-    if (mode != 0 && mode != 1) return set_error("bk_gp_set_var_mode: mode must be 0 (FP64 DMMA) or 1 (int8 tcgen05)");
-    if (mode == 1 && h->n_pad > 16384) return set_error("bk_gp_set_var_mode: int32 accumulation is exact only for n_train <= 16384");
+    if (mode < 0 || mode > 2)
+        return set_error("bk_gp_set_var_mode: mode must be 0 (FP64 DMMA), 1 (int8, 8x7-bit slices) or 2 (int8, 7x8-bit slices)");
+    if (mode == 1 && h->n_pad > 16384) return set_error("bk_gp_set_var_mode: 8x7-bit int32 accumulation is exact only for n_train <= 16384");
+    if (mode == 2 && h->n_pad > 8192) return set_error("bk_gp_set_var_mode: 7x8-bit int32 accumulation is exact only for n_train <= 8192");
+    if (mode == 2)
+        for (int q = 0; q < h->m; ++q)
+            if (h->out[q].c0 < 0.0 || h->out[q].c1 < 0.0)
+                return set_error("bk_gp_set_var_mode: the 7x8-bit scheme slices K* into unsigned bytes and needs c0, c1 >= 0");
     h->var_mode = mode;
     return 0;
 }
@@ -217,7 +224,7 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
     cudaStream_t st = (cudaStream_t)stream;
     if (!std_dev) {
         for (int q = 0; q < h->m; ++q)
-            if (int rc = launch_predict(h, q, pts_dev, k, mean_dev, nullptr, nullptr, 1.0, st)) return rc;
+            if (int rc = launch_predict(h, q, pts_dev, k, mean_dev, nullptr, nullptr, 0, 1.0, st)) return rc;
         return 0;
     }
     const size_t per_point = predict_bytes_per_point(h);
@@ -232,15 +239,16 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
     for (long lo = 0; lo < k; lo += chunk) {
         const long cnt = (k - lo) < chunk ? (k - lo) : chunk;
         for (int q = 0; q < h->m; ++q) {
-            if (h->var_mode == 1) {
+            if (h->var_mode >= 1) {
                 const GpOutput& o = h->out[q];
-                const double kappa = pow2_at_least(fabs(o.c0) + fabs(o.c1));   // |k| <= |c0| + |c1| (stationary factor <= 1)
+                const double kappa = pow2_at_least(fabs(o.c0) + fabs(o.c1));   // |k| <= |c0| + |c1| < kappa (stationary factor <= 1)
+                const int scheme = h->var_mode - 1;
                 if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, nullptr, (int8_t*)kstar,
-                                            kappa, st)) return rc;
-                if (int rc = launch_var_ozaki(h, q, (const int8_t*)kstar, kappa, cnt, std_dev + lo * h->m, scratch,
+                                            scheme, kappa, st)) return rc;
+                if (int rc = launch_var_ozaki(h, q, scheme, (const int8_t*)kstar, kappa, cnt, std_dev + lo * h->m, scratch,
                                               fail_flag, st)) return rc;
             } else {
-                if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, kstar, nullptr, 1.0, st)) return rc;
+                if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, kstar, nullptr, 0, 1.0, st)) return rc;
                 if (int rc = launch_var(h, q, kstar, cnt, std_dev + lo * h->m, st)) return rc;
             }
         }
@@ -264,18 +272,18 @@ int bk_lml_batched(const double* x_dev, const double* y_dev, int n_train, int p,
 
 int bk_gp_factorise(const double* x_dev, const double* y_dev, int n_train, int p, int kind, double c0, double c1,
                     double kdiag, const double* ls_host, double* l_dev, double* alpha_dev, double* w_tiles_dev,
-                    int8_t* wq_dev, double* wsig_dev, double* lml_dev, int* info_dev, void* workspace_dev,
+                    int8_t* wq_dev, double* wsig_dev, int wq_scheme, double* lml_dev, int* info_dev, void* workspace_dev,
                     size_t workspace_bytes, void* stream) {
     if (!x_dev || !y_dev || !ls_host || !l_dev || !alpha_dev || !lml_dev || !info_dev || !workspace_dev)
         return set_error("bk_gp_factorise: NULL pointer");
     return gp_factorise(x_dev, y_dev, n_train, p, kind, c0, c1, kdiag, ls_host, l_dev, alpha_dev, w_tiles_dev, wq_dev,
-                        wsig_dev, lml_dev, info_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+                        wsig_dev, wq_scheme, lml_dev, info_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }
 
 int bk_tri_inverse_pack(const double* l_dev, int n_train, double* w_tiles_dev, int8_t* wq_dev, double* wsig_dev,
-                        void* workspace_dev, size_t workspace_bytes, void* stream) {
+                        int wq_scheme, void* workspace_dev, size_t workspace_bytes, void* stream) {
     if (!l_dev || !w_tiles_dev || !workspace_dev) return set_error("bk_tri_inverse_pack: NULL pointer");
-    return tri_inverse_pack(l_dev, n_train, w_tiles_dev, wq_dev, wsig_dev, workspace_dev, workspace_bytes,
+    return tri_inverse_pack(l_dev, n_train, w_tiles_dev, wq_dev, wsig_dev, wq_scheme, workspace_dev, workspace_bytes,
                             (cudaStream_t)stream);
 }
 

@@ -438,7 +438,7 @@ static int trtri_sweep(const double* M, const double* Winv, double* WT, int n, c
 }
 
 int launch_pack_w_ex(const double* w, int n_rows_valid, int ld, int transposed, double* out, cudaStream_t st);
-int launch_slice_w(const double* src, int n, int ld, int transposed, int8_t* wq, double* wsig, cudaStream_t st);
+int launch_slice_w(const double* src, int n, int ld, int transposed, int scheme, int8_t* wq, double* wsig, cudaStream_t st);
 
 static int build_K(const LmlWorkspace& w, const double* X, int n, int p, int R, cudaStream_t st) {
     const int n_pad = padded_n(n), nP = n_pad / NB;
@@ -476,7 +476,8 @@ int lml_batched(const double* X, const double* y, int n, int p, int R, const int
 // final state at the chosen theta: L (n_pad x n_pad, row-major lower), alpha (n_pad), packed W tiles, lml, info
 int gp_factorise(const double* X, const double* y, int n, int p, int kind, double c0, double c1, double kdiag,
                  const double* ls, double* L_out, double* alpha_out, double* wt_tiles_out, int8_t* wq_out,
-                 double* wsig_out, double* lml_out, int* info_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                 double* wsig_out, int wq_scheme, double* lml_out, int* info_out, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
     if (p > MAX_P) return set_error("p = %d exceeds %d", p, MAX_P);
     if (ws_bytes < lml_workspace_bytes(n, 1, true))
         return set_error("bk_gp_factorise: workspace of %zu bytes needed (got %zu)", lml_workspace_bytes(n, 1, true), ws_bytes);
@@ -498,13 +499,13 @@ int gp_factorise(const double* X, const double* y, int n, int p, int kind, doubl
     if (wt_tiles_out)
         if (int rc = launch_pack_w_ex(WT, n, n_pad, 1, wt_tiles_out, st)) return rc;   // padded rows/cols -> 0
     if (wq_out && wsig_out)
-        if (int rc = launch_slice_w(WT, n, n_pad, 1, wq_out, wsig_out, st)) return rc;
+        if (int rc = launch_slice_w(WT, n, n_pad, 1, wq_scheme, wq_out, wsig_out, st)) return rc;
     return 0;
 }
 
 // W tiles from a given Cholesky factor (models adopted from scikit-learn state)
-int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, int8_t* wq_out, double* wsig_out, void* ws,
-                     size_t ws_bytes, cudaStream_t st) {
+int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, int8_t* wq_out, double* wsig_out, int wq_scheme,
+                     void* ws, size_t ws_bytes, cudaStream_t st) {
     if (ws_bytes < lml_workspace_bytes(n, 1, true))
         return set_error("bk_tri_inverse_pack: workspace of %zu bytes needed (got %zu)", lml_workspace_bytes(n, 1, true), ws_bytes);
     const int n_pad = padded_n(n), nP = n_pad / NB;
@@ -528,7 +529,7 @@ int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, int8_t* wq_ou
     }
     if (int rc = trtri_sweep(w.M, w.Winv, WT, n, st)) return rc;
     if (wq_out && wsig_out)
-        if (int rc = launch_slice_w(WT, n, n_pad, 1, wq_out, wsig_out, st)) return rc;
+        if (int rc = launch_slice_w(WT, n, n_pad, 1, wq_scheme, wq_out, wsig_out, st)) return rc;
     return launch_pack_w_ex(WT, n, n_pad, 1, wt_tiles_out, st);   // padded rows/cols -> 0
 }
 

@@ -39,7 +39,8 @@ struct PredictParams {
     double inv_kappa;      // 1 / (power of two >= max |k|)
 };
 
-// WRITE_K: 0 = mean only, 1 = K* as FP64 DMMA fragment tiles (gp_var.cu), 2 = K* as int8 slices (var_ozaki.cu)
+// WRITE_K: 0 = mean only, 1 = K* as FP64 DMMA fragment tiles (gp_var.cu), 2 = K* as 8 signed 7-bit int8 slices,
+// 3 = K* as 7 unsigned byte slices (var_ozaki.cu schemes 0 / 1)
 template <int KIND, int P, int WRITE_K>
 __global__ void __launch_bounds__(PRED_THREADS) k_predict(const PredictParams<P> prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(const PredictParams<P>
     // K* destination of this thread (see gp_var.cu for the tile layout)
     double* kdst[PRED_TP];
     int8_t* qdst[PRED_TP];
-    if constexpr (WRITE_K == 2) {
+    if constexpr (WRITE_K >= 2) {
 #pragma unroll
         for (int e = 0; e < PRED_TP; ++e) {
             const long t = t_idx[e];
@@ -181,6 +182,38 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(const PredictParams<P>
                     for (int a = 0; a < 8; ++a) *reinterpret_cast<uint2*>(d + (size_t)a * 4096) = make_uint2(pk[a][0], pk[a][1]);
                 }
             }
+            if constexpr (WRITE_K == 3) {
+                // unsigned byte slicing: X = rint(k/kappa * 2^56) in [0, 2^56) = hi * 2^28 + lo; slice b = byte 7-b of X
+                const int jg = tile * PRED_TJ + j8;
+#pragma unroll
+                for (int e = 0; e < PRED_TP; ++e) {
+                    unsigned int pk[7][2];
+#pragma unroll
+                    for (int a = 0; a < 7; ++a) pk[a][0] = pk[a][1] = 0u;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const double x28 = __dmul_rn(__dmul_rn(kbuf[e][jj], prm.inv_kappa), 0x1p28);
+                        const double hm = __dadd_rn(x28, 6755399441055744.0);
+                        int hi = __double2loint(hm);                                  // rint(x * 2^28) in [0, 2^28]
+                        const double r28 = __dmul_rn(__dadd_rn(x28, -__dadd_rn(hm, -6755399441055744.0)), 0x1p28);
+                        int lo = __double2loint(__dadd_rn(r28, 6755399441055744.0));  // in [-2^27, 2^27]
+                        if (lo < 0) { lo += 1 << 28; hi -= 1; }                       // 0 <= lo < 2^28
+                        if (hi < 0) { hi = 0; lo = 0; }                               // k slightly below 0 by rounding: clamp
+                        const unsigned int uh = (unsigned int)hi, ul = (unsigned int)lo;
+                        const int sh = 8 * (jj & 3), w = jj >> 2;
+                        pk[0][w] |= ((uh >> 20) & 255u) << sh;                        // bits 48..55
+                        pk[1][w] |= ((uh >> 12) & 255u) << sh;
+                        pk[2][w] |= ((uh >> 4) & 255u) << sh;
+                        pk[3][w] |= ((((uh & 15u) << 4) | (ul >> 24)) & 255u) << sh;   // bits 24..31
+                        pk[4][w] |= ((ul >> 16) & 255u) << sh;
+                        pk[5][w] |= ((ul >> 8) & 255u) << sh;
+                        pk[6][w] |= (ul & 255u) << sh;                                // bits 0..7
+                    }
+                    int8_t* d = qdst[e] + (size_t)(jg >> 5) * 8 * 4096 + ((jg & 31) >> 4) * 128 + (jg & 15);
+#pragma unroll
+                    for (int a = 0; a < 7; ++a) *reinterpret_cast<uint2*>(d + (size_t)a * 4096) = make_uint2(pk[a][0], pk[a][1]);
+                }
+            }
             if constexpr (WRITE_K == 1) {
                 const int jg = tile * PRED_TJ + j8;          // global train index of kbuf[.][0]
 #pragma unroll
@@ -213,7 +246,7 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(const PredictParams<P>
 
 template <int KIND, int P>
 static int launch_predict_kp(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar,
-                             int8_t* kq, double kappa, cudaStream_t st) {
+                             int8_t* kq, int kq_scheme, double kappa, cudaStream_t st) {
     const GpOutput& o = h->out[q];
     PredictParams<P> prm;
     prm.pts = pts; prm.k = k; prm.p = h->p; prm.n_pad = h->n_pad;
@@ -230,7 +263,10 @@ static int launch_predict_kp(const bk_gp_s* h, int q, const double* pts, long k,
     // with K* output every 128-point tile must be fully written: round the grid up to whole tiles
     const unsigned grid = (unsigned)((k + per_cta - 1) / per_cta);
     ProfScope prof(PROF_PREDICT, st);
-    if (kq) {
+    if (kq && kq_scheme == 1) {
+        BK_CUDA(cudaFuncSetAttribute(k_predict<KIND, P, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_predict<KIND, P, 3><<<grid, PRED_THREADS, smem, st>>>(prm);
+    } else if (kq) {
         BK_CUDA(cudaFuncSetAttribute(k_predict<KIND, P, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_predict<KIND, P, 2><<<grid, PRED_THREADS, smem, st>>>(prm);
     } else if (kstar) {
@@ -246,18 +282,18 @@ static int launch_predict_kp(const bk_gp_s* h, int q, const double* pts, long k,
 
 template <int KIND>
 static int launch_predict_k(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar,
-                            int8_t* kq, double kappa, cudaStream_t st) {
+                            int8_t* kq, int kq_scheme, double kappa, cudaStream_t st) {
     switch (h->P) {
-        case 2: return launch_predict_kp<KIND, 2>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case 4: return launch_predict_kp<KIND, 4>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case 6: return launch_predict_kp<KIND, 6>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case 8: return launch_predict_kp<KIND, 8>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case 10: return launch_predict_kp<KIND, 10>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case 12: return launch_predict_kp<KIND, 12>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case 16: return launch_predict_kp<KIND, 16>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case 20: return launch_predict_kp<KIND, 20>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case 24: return launch_predict_kp<KIND, 24>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case 32: return launch_predict_kp<KIND, 32>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case 2: return launch_predict_kp<KIND, 2>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case 4: return launch_predict_kp<KIND, 4>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case 6: return launch_predict_kp<KIND, 6>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case 8: return launch_predict_kp<KIND, 8>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case 10: return launch_predict_kp<KIND, 10>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case 12: return launch_predict_kp<KIND, 12>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case 16: return launch_predict_kp<KIND, 16>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case 20: return launch_predict_kp<KIND, 20>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case 24: return launch_predict_kp<KIND, 24>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case 32: return launch_predict_kp<KIND, 32>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
     }
     return set_error("unsupported padded dimension %d", h->P);
 }
@@ -279,13 +315,13 @@ int launch_debug_fastmath(const double* in, long n, double* o_sqrt, double* o_ex
 
 // mean of output q at k points; if kstar != null also the packed K* tiles for gp_var
 int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar, int8_t* kq,
-                   double kappa, cudaStream_t st) {
+                   int kq_scheme, double kappa, cudaStream_t st) {
     switch (h->out[q].kind) {
-        case BK_MATERN12: return launch_predict_k<BK_MATERN12>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case BK_MATERN32: return launch_predict_k<BK_MATERN32>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case BK_MATERN52: return launch_predict_k<BK_MATERN52>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case BK_RBF: return launch_predict_k<BK_RBF>(h, q, pts, k, mean, kstar, kq, kappa, st);
-        case BK_MATERN_INF: return launch_predict_k<BK_MATERN_INF>(h, q, pts, k, mean, kstar, kq, kappa, st);
+        case BK_MATERN12: return launch_predict_k<BK_MATERN12>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case BK_MATERN32: return launch_predict_k<BK_MATERN32>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case BK_MATERN52: return launch_predict_k<BK_MATERN52>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case BK_RBF: return launch_predict_k<BK_RBF>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case BK_MATERN_INF: return launch_predict_k<BK_MATERN_INF>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
     }
     return set_error("output %d has no kernel set", q);
 }

@@ -13,8 +13,9 @@
 // L2-resident scratch tile and added in pass 1.
 //   warp 5 lane 0 : TMA producer  (cp.async.bulk of pre-packed slice tiles, 6-slot full/empty mbarrier ring)
 //   warp 4 lane 0 : MMA issuer    (tcgen05.mma.cta_group::1.kind::i8, M128 N128 K32, SMEM descriptors, commit)
-//   warps 0..3    : epilogue      (tcgen05.ld -> exact int64 combine -> FP64 -> sum of v^2; one thread per test
-//                                  point: TMEM lanes = test points (M side = K* slices), columns = W rows (N side))
+//   warps 0..3, 6..9 : epilogue   (tcgen05.ld -> exact int64 combine -> FP64 -> sum of v^2; TMEM lanes = test points
+//                                  (M side = K* slices), columns = W rows (N side); two threads per test point, each
+//                                  draining half of the columns, software-pipelined TMEM reads, no cross-thread reduction)
 // Operand tiles are packed on the producer side (W at upload, K* by K1) in the non-swizzled K-major UMMA
 // layout: element (row r, byte b) of a 128 x 32 B tile at (r/8)*256 + (b/16)*128 + (r%8)*16 + b%16.
 #include <stdlib.h>
@@ -29,7 +30,7 @@ constexpr int OZ_TILE = 4096;                 // bytes of one 128 x 32 B slice t
 constexpr int OZ_SLOTS = 6;                   // ring of 32 KiB slots (8 slice tiles each)
 constexpr int OZ_SLOT_BYTES = OZ_S * OZ_TILE; // pass 0: one slot per k slab = [A slices 1..4 | B slices 1..4]
                                               // pass 1: two slots per k slab = [A slices 1..8], [B slices 1..8]
-constexpr int OZ_THREADS = 192;
+constexpr int OZ_THREADS = 320;                // warps 0-3 and 6-9: epilogue (two column halves); warp 4: MMA; warp 5: TMA
 constexpr size_t OZ_SMEM = (size_t)OZ_SLOTS * OZ_SLOT_BYTES + 4 * 32 * 17 * 8 + 4 * 128 * 8 + 2 * OZ_SLOTS * 8 + 64 + 1024;
 
 __device__ __forceinline__ uint64_t oz_desc(uint32_t smem_addr) {
@@ -57,16 +58,26 @@ __device__ __forceinline__ bool oz_wait(uint64_t* bar, uint32_t parity, int* fai
     return true;
 }
 
-// All slice pairs (a, b), a + b = g, of the four accumulator groups of one pass for one k slab, fully unrolled:
-// per MMA the issuing thread only adds a tile offset to two pre-built descriptors (start-address field, 16-B units).
+// Two error-free slicings (SCHEME):
+//   0: 8 x 7-bit signed digits for both operands; group g = a + b has weight 2^-(7g-2); 36 pairs with g <= 9;
+//      pass 0 = groups 2..5, pass 1 = groups 6..9; int32 exact for n <= 16384.
+//   1: 7 x 8-bit digits, W signed (|w| < 1/2, X = rint(w 2^55)), K* unsigned bytes (0 <= x < 1, X = rint(x 2^56));
+//      group g has weight 2^(1-8g); 28 pairs with g <= 8; pass 0 = groups 2..5, pass 1 = groups 6..8;
+//      int32 exact for n <= 8192; needs k >= 0 (c0, c1 >= 0).  22 % fewer MMAs, byte-extraction slicing in K1.
+template <int SCHEME> struct OzTraits;
+template <> struct OzTraits<0> { static constexpr int S = 8, BITS = 7, G_END = 10; };   // groups 2 .. G_END-1
+template <> struct OzTraits<1> { static constexpr int S = 7, BITS = 8, G_END = 9; };
+
+// All slice pairs (a, b), a + b = g, of the accumulator groups of one pass for one k slab, fully unrolled: per MMA
+// the issuing thread only adds a tile offset to two pre-built descriptors (start-address field, 16-B units).
 // M side (TMEM lanes) = the 128 test points (K* slices), N side (TMEM columns) = the 128 rows of the W panel.
-template <int PASS>
+template <int SCHEME, int PASS>
 __device__ __forceinline__ void oz_issue_slab(uint32_t tmem_base, uint64_t kdesc0, uint64_t wdesc0, uint32_t idesc,
                                               uint32_t not_first) {
-    constexpr int G_LO = PASS == 0 ? 2 : 6;
+    constexpr int S = OzTraits<SCHEME>::S;
+    constexpr int G_LO = PASS == 0 ? 2 : 6, G_HI = PASS == 0 ? 6 : OzTraits<SCHEME>::G_END;
 #pragma unroll
-    for (int g = G_LO; g < G_LO + 4; ++g) {
-        constexpr int S = OZ_S;
+    for (int g = G_LO; g < G_HI; ++g) {
 #pragma unroll
         for (int a = 1; a <= S; ++a) {
             const int b = g - a;                       // a = W slice, b = K* slice
@@ -79,14 +90,21 @@ __device__ __forceinline__ void oz_issue_slab(uint32_t tmem_base, uint64_t kdesc
     }
 }
 
+__device__ __forceinline__ double oz_i64_to_double(long long h) {    // exact for |h| < 2^51; no I2F.F64
+    return __longlong_as_double(h + 0x4338000000000000ll) - 6755399441055744.0;
+}
+
+template <int SCHEME>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, const int8_t* __restrict__ kq,
             int n_pad, double kappa, double kdiag, double y_std, double* __restrict__ scratch,
             double* __restrict__ std_out, long k, int ld, int q, int* __restrict__ fail_flag, int dbg) {
+    constexpr int S = OzTraits<SCHEME>::S, BITS = OzTraits<SCHEME>::BITS;
+    constexpr int NG1 = OzTraits<SCHEME>::G_END - 6;                 // accumulator groups of pass 1 (4 or 3)
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stages = smem;
-    double* red = reinterpret_cast<double*>(smem + (size_t)OZ_SLOTS * OZ_SLOT_BYTES);         // [4 warps][32][17]
-    double* colred = red + 4 * 32 * 17;                                                       // [4][128]
+    double* red = reinterpret_cast<double*>(smem + (size_t)OZ_SLOTS * OZ_SLOT_BYTES);         // [128] row scales (+ spare)
+    double* colred = red + 4 * 32 * 17;                                                       // [128]
     uint64_t* full = reinterpret_cast<uint64_t*>(colred + 4 * 128);                           // [slots]
     uint64_t* empty = full + OZ_SLOTS;                                                        // [slots]
     uint64_t* acc_full = empty + OZ_SLOTS;
@@ -102,7 +120,7 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
     if (tid == 0) {
         for (int s = 0; s < OZ_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 4);
+        mbar_init(acc_empty, 8);
         mbar_fence_init();
         fail_s = 0;
     }
@@ -139,7 +157,7 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
                         if (pass == 0) {
                             fill(a_src, 4 * OZ_TILE, b_src, 4 * OZ_TILE);
                         } else {
-                            if (fill(a_src, OZ_S * OZ_TILE, nullptr, 0)) fill(b_src, OZ_S * OZ_TILE, nullptr, 0);
+                            if (fill(a_src, S * OZ_TILE, nullptr, 0)) fill(b_src, S * OZ_TILE, nullptr, 0);
                         }
                     }
             if (fail) fail_s = 1;
@@ -148,15 +166,15 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
         // ================= MMA issuer =================
         if (lane == 0) {
             int fail = 0;
-            // instruction descriptor: S32 accumulate, signed int8 A and B, K-major both, N = 128, M = 128
-            const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+            // instruction descriptor: S32 accumulate; A = K* slices (signed, or unsigned bytes in scheme 1), B = W slices
+            // (signed); K-major both; N = 128, M = 128
+            const uint32_t idesc = (2u << 4) | ((SCHEME == 0 ? 1u : 0u) << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
             long u = 0;
             int round = 0;                                                   // (panel, pass) counter
             for (int panel = 0; panel < n_panels && !fail; ++panel)
                 for (int pass = 0; pass < 2 && !fail; ++pass, ++round) {
                     if (round > 0 && !oz_wait(acc_empty, (uint32_t)((round - 1) & 1), &fail)) break;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const int g_lo = pass == 0 ? 2 : 6;
                     const int nks_p = (panel + 1) * 4;
                     for (int ks = 0; ks < nks_p; ++ks) {
                         const int s0 = (int)(u % OZ_SLOTS), s1 = (int)((u + 1) % OZ_SLOTS);
@@ -165,8 +183,8 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t w_base = smem_u32(stages + (size_t)s0 * OZ_SLOT_BYTES);
                         const uint32_t k_base = pass == 0 ? w_base + 4 * OZ_TILE : smem_u32(stages + (size_t)s1 * OZ_SLOT_BYTES);
-                        if (pass == 0) oz_issue_slab<0>(tmem_base, oz_desc(k_base), oz_desc(w_base), idesc, ks > 0 ? 1u : 0u);
-                        else oz_issue_slab<1>(tmem_base, oz_desc(k_base), oz_desc(w_base), idesc, ks > 0 ? 1u : 0u);
+                        if (pass == 0) oz_issue_slab<SCHEME, 0>(tmem_base, oz_desc(k_base), oz_desc(w_base), idesc, ks > 0 ? 1u : 0u);
+                        else oz_issue_slab<SCHEME, 1>(tmem_base, oz_desc(k_base), oz_desc(w_base), idesc, ks > 0 ? 1u : 0u);
                         oz_commit(&empty[s0]);                               // slot(s) free once these MMAs retire
                         if (pass == 1) oz_commit(&empty[s1]);
                         u += pass == 0 ? 1 : 2;
@@ -176,61 +194,103 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
             if (fail) fail_s = 1;
         }
     } else {
-        // ================= epilogue warps 0..3: TMEM lane 32*warp + lane = test point, columns = rows of the W panel ====
+        // ================= epilogue: warps 0..3 drain W-row columns 0..63 of every group, warps 6..9 columns 64..127.
+        // A warp may only touch TMEM lanes 32*(warp%4)..+31, so thread (warp%4, lane) owns test point 32*(warp%4)+lane.
         int fail = 0;
-        double vsum = 0.0;                                  // sum_i v_i^2 of this thread's test point
-        const int tp = warp * 32 + lane;
+        double vsum = 0.0;                                  // sum over this thread's W rows of v^2 for its test point
+        const int half = warp < 4 ? 0 : 1;
+        const int tp = (warp & 3) * 32 + lane;
         double* sigs = red;                                 // [128] sigma_i * kappa of the current panel
+        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
         int round = 0;
+        auto load_chunk = [&](uint32_t (&d)[4][16], int c, int ng) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                if (g < ng) {
+                    const uint32_t taddr = lane_base + (uint32_t)(g * 128 + c * 16);
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                 : "=r"(d[g][0]), "=r"(d[g][1]), "=r"(d[g][2]), "=r"(d[g][3]), "=r"(d[g][4]),
+                                   "=r"(d[g][5]), "=r"(d[g][6]), "=r"(d[g][7]), "=r"(d[g][8]), "=r"(d[g][9]),
+                                   "=r"(d[g][10]), "=r"(d[g][11]), "=r"(d[g][12]), "=r"(d[g][13]), "=r"(d[g][14]),
+                                   "=r"(d[g][15])
+                                 : "r"(taddr));
+                }
+            }
+        };
+        auto process_chunk = [&](const uint32_t (&d)[4][16], int c, int pass) {
+            double sv[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sv[j] = pass == 1 ? scr[(size_t)(c * 16 + j) * 128 + tp] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                // Combine the groups of the pass EXACTLY in int64 (weights 2^-BITS apart), then integer add + DADD
+                // converts to FP64 (I2F.F64 is slow).  The scale of the LAST group of the pass applies.
+                double h;
+                if (pass == 0) {
+                    if constexpr (SCHEME == 0) {         // |D| < 2^29: 21 + 29 < 51 bits
+                        h = oz_i64_to_double(((long long)(int)d[0][j] << 21) + ((long long)(int)d[1][j] << 14) +
+                                             ((long long)(int)d[2][j] << 7) + (long long)(int)d[3][j]) * 0x1p-33;
+                    } else {                             // |D| < 2^31: two exact halves, 2^16 apart; group 5 weight 2^(1-40)
+                        const double ha = oz_i64_to_double(((long long)(int)d[0][j] << 8) + (long long)(int)d[1][j]);
+                        const double hb = oz_i64_to_double(((long long)(int)d[2][j] << 8) + (long long)(int)d[3][j]);
+                        h = fma(ha, 0x1p16, hb) * 0x1p-39;
+                    }
+                    scr[(size_t)(c * 16 + j) * 128 + tp] = h;
+                } else {
+                    if constexpr (SCHEME == 0) {
+                        h = oz_i64_to_double(((long long)(int)d[0][j] << 21) + ((long long)(int)d[1][j] << 14) +
+                                             ((long long)(int)d[2][j] << 7) + (long long)(int)d[3][j]) * 0x1p-61;
+                    } else {                             // groups 6..8: 16 + 31 < 51 bits; group 8 weight 2^(1-64)
+                        h = oz_i64_to_double(((long long)(int)d[0][j] << 16) + ((long long)(int)d[1][j] << 8) +
+                                             (long long)(int)d[2][j]) * 0x1p-63;
+                    }
+                    const double v = sigs[c * 16 + j] * (h + sv[j]);
+                    vsum = fma(v, v, vsum);
+                }
+            }
+        };
         for (int panel = 0; panel < n_panels && !fail; ++panel)
             for (int pass = 0; pass < 2 && !fail; ++pass, ++round) {
                 if (pass == 1) {
-                    // named barrier among the 4 epilogue warps: previous panel's sigs fully consumed, then refill
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    sigs[tp] = wsig[panel * 128 + tp] * kappa;
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    // named barrier among the 8 epilogue warps: previous panel's sigs fully consumed, then refill
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if (half == 0) sigs[tp] = wsig[panel * 128 + tp] * kappa;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
                 if (!oz_wait(acc_full, (uint32_t)(round & 1), &fail)) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-                for (int c = 0; c < ((dbg & 1) ? 0 : 8); ++c) {   // 16 W rows at a time (dbg bit 0: timing experiment, no drain)
-                    double sv[16];                          // pass-0 partials of this chunk: loads fly under the TMEM read
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) sv[j] = pass == 1 ? scr[(size_t)(c * 16 + j) * 128 + tp] : 0.0;
-                    uint32_t d[4][16];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(g * 128 + c * 16);
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                                     : "=r"(d[g][0]), "=r"(d[g][1]), "=r"(d[g][2]), "=r"(d[g][3]), "=r"(d[g][4]),
-                                       "=r"(d[g][5]), "=r"(d[g][6]), "=r"(d[g][7]), "=r"(d[g][8]), "=r"(d[g][9]),
-                                       "=r"(d[g][10]), "=r"(d[g][11]), "=r"(d[g][12]), "=r"(d[g][13]), "=r"(d[g][14]),
-                                       "=r"(d[g][15])
-                                     : "r"(taddr));
-                    }
+                const bool skip = (dbg & 1) || (pass == 0 && (dbg & 4)) || (pass == 1 && (dbg & 8));   // timing experiments
+                if (!skip) {
+                    // 4 chunks of 16 W rows per half, software pipelined: the TMEM read of chunk c+1 flies under the
+                    // arithmetic of chunk c (tcgen05.wait::ld waits for everything issued so far)
+                    const int ng = pass == 0 ? 4 : NG1;
+                    const int c0 = half * 4;
+                    uint32_t da[4][16], db[4][16];
+                    load_chunk(da, c0, ng);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        // Combine the four groups of the pass EXACTLY in int64 (weights 2^-7 apart; |D_g| < 2^29 so
-                        // |h| < 2^51), then one integer add + one DADD converts to FP64 (I2F.F64 is slow).
-                        const long long h64 = ((long long)(int)d[0][j] << 21) + ((long long)(int)d[1][j] << 14) +
-                                              ((long long)(int)d[2][j] << 7) + (long long)(int)d[3][j];
-                        const double h = __longlong_as_double(h64 + 0x4338000000000000ll) - 6755399441055744.0;
-                        if (pass == 0) {
-                            scr[(size_t)(c * 16 + j) * 128 + tp] = h * 0x1p-33;          // groups 2..5: 2^-12 * 2^-21
-                        } else {
-                            const double v = sigs[c * 16 + j] * fma(h, 0x1p-61, sv[j]);  // groups 6..9: 2^-40 * 2^-21
-                            vsum = fma(v, v, vsum);
-                        }
-                    }
+                    load_chunk(db, c0 + 1, ng);
+                    process_chunk(da, c0, pass);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    load_chunk(da, c0 + 2, ng);
+                    process_chunk(db, c0 + 1, pass);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    load_chunk(db, c0 + 3, ng);
+                    process_chunk(da, c0 + 2, pass);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // every TMEM read of this round is complete: release the accumulators before the last arithmetic
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
+                    process_chunk(db, c0 + 3, pass);
+                } else {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acc_empty);
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty);
             }
         if (fail) fail_s = 1;
-        colred[tp] = vsum;
+        colred[half * 128 + tp] = vsum;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -238,7 +298,7 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
     if (tid < 128) {
         const long t = (long)blockIdx.x * 128 + tid;
         if (t < k) {
-            double var = __dadd_rn(kdiag, -colred[tid]);                                       // sklearn:_gpr.py:480-481
+            double var = __dadd_rn(kdiag, -(colred[tid] + colred[128 + tid]));         // sklearn:_gpr.py:480-481
             if (var < 0.0) var = 0.0;                                                  // :485-491
             std_out[t * ld + q] = sqrt(__dmul_rn(var, __dmul_rn(y_std, y_std)));       // :494,500
         }
@@ -247,8 +307,8 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
 }
 
 // ---------------------------------------------------------------- W -> row scales + int8 slices (upload time)
-// src: row-major n_pad-strided lower-triangular W (transposed = 1: src holds W^T).  One warp per row.
-__global__ void k_slice_w(const double* __restrict__ src, int n, int ld, int transposed, int n_pad,
+// src: row-major ld-strided lower-triangular W (transposed = 1: src holds W^T).  One warp per row.
+__global__ void k_slice_w(const double* __restrict__ src, int n, int ld, int transposed, int n_pad, int scheme,
                           int8_t* __restrict__ wq, double* __restrict__ wsig) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= n_pad) return;
@@ -263,7 +323,7 @@ __global__ void k_slice_w(const double* __restrict__ src, int n, int ld, int tra
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     int e = 0;
     double sig = 1.0;
-    if (mx > 0.0) { frexp(mx, &e); sig = ldexp(1.0, e); }    // mx = f * 2^e with f in [0.5, 1)  ->  |w| / sig < 1
+    if (mx > 0.0) { frexp(mx, &e); sig = ldexp(1.0, e + (scheme == 1 ? 1 : 0)); }   // |w|/sig < 1 (scheme 0) or < 1/2 (scheme 1)
     if (lane == 0) wsig[row] = sig;
     const double inv = 1.0 / sig;                           // power of two: exact
     const int panel = row >> 7, r = row & 127;
@@ -272,38 +332,55 @@ __global__ void k_slice_w(const double* __restrict__ src, int n, int ld, int tra
         if (row < n && j <= row) w = (transposed ? src[(size_t)j * ld + row] : src[(size_t)row * ld + j]) * inv;
         const int ks = j >> 5, b = j & 31;
         int8_t* base = wq + ((size_t)panel * nks + ks) * OZ_S * OZ_TILE + (r >> 3) * 256 + (b >> 4) * 128 + (r & 7) * 16 + (b & 15);
-        double y = w * 64.0;
+        if (scheme == 0) {                                  // 8 x 7-bit digits, greedy from the top (all exact in FP64)
+            double y = w * 64.0;
 #pragma unroll
-        for (int a = 0; a < OZ_S; ++a) {
-            const double qd = rint(y);
-            base[(size_t)a * OZ_TILE] = (int8_t)(int)qd;
-            y = (y - qd) * 128.0;                           // exact: |y - qd| <= 1/2
+            for (int a = 0; a < 8; ++a) {
+                const double qd = rint(y);
+                base[(size_t)a * OZ_TILE] = (int8_t)(int)qd;
+                y = (y - qd) * 128.0;                       // exact: |y - qd| <= 1/2
+            }
+        } else {                                            // 7 signed base-256 digits of X = rint(w 2^55), |X| < 2^54
+            long long X = llrint(w * 0x1p55);
+#pragma unroll
+            for (int a = 6; a >= 1; --a) {
+                const long long dg = ((X + 128) & 255) - 128;
+                base[(size_t)a * OZ_TILE] = (int8_t)dg;
+                X = (X - dg) >> 8;
+            }
+            base[0] = (int8_t)X;                            // |X| <= 64
+            base[(size_t)7 * OZ_TILE] = 0;
         }
     }
 }
 
-int launch_slice_w(const double* src, int n, int ld, int transposed, int8_t* wq, double* wsig, cudaStream_t st) {
+int launch_slice_w(const double* src, int n, int ld, int transposed, int scheme, int8_t* wq, double* wsig, cudaStream_t st) {
     const int n_pad = padded_n(n);
     ProfScope prof(PROF_OTHER, st);
-    k_slice_w<<<(n_pad + 7) / 8, 256, 0, st>>>(src, n, ld, transposed, n_pad, wq, wsig);
+    k_slice_w<<<(n_pad + 7) / 8, 256, 0, st>>>(src, n, ld, transposed, n_pad, scheme, wq, wsig);
     BK_LAUNCH_CHECK("k_slice_w");
     return 0;
 }
 
-int launch_var_ozaki(const bk_gp_s* h, int q, const int8_t* kq, double kappa, long k, double* std_out,
+int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, double kappa, long k, double* std_out,
                      double* scratch, int* fail_flag, cudaStream_t st) {
     const GpOutput& o = h->out[q];
     if (!o.wq || !o.wsig) return set_error("int8 variance path requested but output %d has no sliced L^-1", q);
     static bool attr_set = false;
     if (!attr_set) {
-        BK_CUDA(cudaFuncSetAttribute(k_var_ozaki, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+        BK_CUDA(cudaFuncSetAttribute(k_var_ozaki<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
+        BK_CUDA(cudaFuncSetAttribute(k_var_ozaki<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
         attr_set = true;
     }
     const unsigned grid = (unsigned)((k + 127) / 128);
-    ProfScope prof(PROF_VAR, st);
     static int dbg = getenv("BK_OZ_DBG") ? atoi(getenv("BK_OZ_DBG")) : 0;
-    k_var_ozaki<<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std, scratch, std_out,
-                                                   k, h->m, q, fail_flag, dbg);
+    ProfScope prof(PROF_VAR, st);
+    if (scheme == 1)
+        k_var_ozaki<1><<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std, scratch,
+                                                          std_out, k, h->m, q, fail_flag, dbg);
+    else
+        k_var_ozaki<0><<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std, scratch,
+                                                          std_out, k, h->m, q, fail_flag, dbg);
     BK_LAUNCH_CHECK("k_var_ozaki");
     return 0;
 }

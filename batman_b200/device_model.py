@@ -62,19 +62,36 @@ class DeviceModel:
                 self.xs.append(xs)
                 self.alpha.append(al)
                 self._set_output(q)
+        from .lml import int8_scheme
+        self.int8_scheme = int8_scheme(self.n, specs)    # the fit slices L^-1 with the same rule
+        self._forced_scheme = os.environ.get('BATMAN_B200_INT8_SCHEME')
         self._workspace = None
         self._scaler = None
         self.sigma_kernel = 'dmma'
         # default: the int8 tensor-core kernel (exact slicing, float64-equivalent results, 1.2-1.6x faster);
         # BATMAN_B200_SIGMA=dmma selects the FP64 DMMA kernel, which also serves n_train > 16384
         self.set_sigma_kernel(os.environ.get('BATMAN_B200_SIGMA', 'int8' if self.n_pad <= 16384 else 'dmma'))
+        if self._forced_scheme is not None and int(self._forced_scheme) != self.int8_scheme and self._Ls is not None:
+            self.set_int8_scheme(int(self._forced_scheme))
 
     def set_sigma_kernel(self, name):
-        """'dmma' = FP64 tensor cores (k_var_trmm); 'int8' = tcgen05 int8 + TMEM, error-free slicing (k_var_ozaki)."""
+        """'dmma' = FP64 tensor cores (k_var_trmm); 'int8' = tcgen05 int8 + TMEM, error-free slicing (k_var_ozaki;
+        8 x 7-bit or 7 x 8-bit slices, see lml.int8_scheme)."""
         if name not in ('dmma', 'int8'):
             raise ValueError("sigma kernel must be 'dmma' or 'int8'")
-        _lib.check(self.lib.bk_gp_set_var_mode(self.handle, 1 if name == 'int8' else 0))
+        _lib.check(self.lib.bk_gp_set_var_mode(self.handle, 1 + self.int8_scheme if name == 'int8' else 0))
         self.sigma_kernel = name
+
+    def set_int8_scheme(self, scheme):
+        """Force the slicing scheme of the int8 sigma kernel (0: 8 x 7-bit, 1: 7 x 8-bit); L^-1 is re-sliced."""
+        if scheme not in (0, 1):
+            raise ValueError("int8 scheme must be 0 or 1")
+        if self._Ls is None:
+            raise RuntimeError("re-slicing needs the Cholesky factor")
+        self.int8_scheme = scheme
+        self.wt, self.wq, self.wsig = [None] * self.m, [None] * self.m, [None] * self.m
+        self.ensure_w()
+        self.set_sigma_kernel(self.sigma_kernel)
 
     # -- C handle ------------------------------------------------------------------------------
     def _set_output(self, q):
@@ -102,7 +119,7 @@ class DeviceModel:
         from .lml import inverse_tiles
         for q in range(self.m):
             if self.wt[q] is None:
-                self.wt[q], self.wq[q], self.wsig[q] = inverse_tiles(self._Ls[q], self.device)
+                self.wt[q], self.wq[q], self.wsig[q] = inverse_tiles(self._Ls[q], self.device, self.int8_scheme)
                 self._set_output(q)
 
     def close(self):

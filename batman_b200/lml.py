@@ -61,6 +61,13 @@ def lml_batched(X_dev, y_dev, specs):
     return out
 
 
+def int8_scheme(n, specs):
+    """Slicing scheme of the int8 sigma kernel for a model: 1 (7 x 8-bit, fewer MMAs) when the int32 accumulation
+    stays exact (n_pad <= 8192) and every covariance is non-negative (K* is sliced into unsigned bytes), else 0."""
+    n_pad = _lib.load().bk_gp_padded_n(n)
+    return 1 if n_pad <= 8192 and all(s.c0 >= 0.0 and s.c1 >= 0.0 for s in specs) else 0
+
+
 def factorise(X_dev, y_dev, spec):
     """Final state at the chosen theta (sklearn:_gpr.py:349-367).
 
@@ -82,7 +89,8 @@ def factorise(X_dev, y_dev, spec):
         info = torch.zeros(1, dtype=torch.int32, device=dev)
         _lib.check(lib.bk_gp_factorise(_ptr(X_dev), _ptr(y_dev), n, p, spec.kind, spec.c0, spec.c1, spec.kdiag,
                                        _lib.as_double_array(spec.ls), _ptr(L), _ptr(alpha), _ptr(wt), _ptr(wq),
-                                       _ptr(wsig), _ptr(lml), _ptr(info), _ptr(ws), ws.numel(), _stream()))
+                                       _ptr(wsig), int8_scheme(n, [spec]), _ptr(lml), _ptr(info), _ptr(ws), ws.numel(),
+                                       _stream()))
         if int(info.item()) != 0:
             raise np.linalg.LinAlgError(
                 "The kernel is not returning a positive definite matrix. Try gradually increasing the "
@@ -91,7 +99,7 @@ def factorise(X_dev, y_dev, spec):
         return L_host, alpha[:n].cpu().numpy(), float(lml.item()), (wt, wq, wsig)
 
 
-def inverse_tiles(L_host, device):
+def inverse_tiles(L_host, device, scheme=0):
     """L^-1 from a given Cholesky factor (models adopted from scikit-learn state): FP64 DMMA tiles, int8 slices
     and their row scales."""
     lib = _lib.load()
@@ -102,6 +110,7 @@ def inverse_tiles(L_host, device):
         wt = torch.empty(lib.bk_gp_wtiles_len(n), dtype=torch.float64, device=device)
         wq = torch.empty(lib.bk_gp_wq_bytes(n), dtype=torch.int8, device=device)
         wsig = torch.empty(lib.bk_gp_padded_n(n), dtype=torch.float64, device=device)
-        _lib.check(lib.bk_tri_inverse_pack(_ptr(L), n, _ptr(wt), _ptr(wq), _ptr(wsig), _ptr(ws), ws.numel(), _stream()))
+        _lib.check(lib.bk_tri_inverse_pack(_ptr(L), n, _ptr(wt), _ptr(wq), _ptr(wsig), scheme, _ptr(ws), ws.numel(),
+                                           _stream()))
         torch.cuda.current_stream().synchronize()
     return wt, wq, wsig

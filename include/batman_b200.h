@@ -71,8 +71,11 @@ int bk_gp_set_output(bk_gp_t h, int q, int kind, double c0, double c1, double kd
                      const double* w_tiles_dev, double y_mean, double y_std);
 /* Optional int8 image of L^-1 for the tcgen05 variance kernel (error-free 8 x 7-bit slicing, csrc/var_ozaki.cu):
  * wq_dev bk_gp_wq_bytes(n) bytes of slice tiles, wsig_dev n_pad power-of-two row scales; both produced by
- * bk_tri_inverse_pack / bk_gp_factorise.  bk_gp_set_var_mode selects the sigma kernel: 0 = FP64 DMMA (default),
- * 1 = int8 tensor cores + TMEM (same results to ~1e-14 of the prior variance; n_train <= 16384). */
+ * bk_tri_inverse_pack / bk_gp_factorise with wq_scheme 0 (8 signed 7-bit slices, n_train <= 16384) or 1 (7 8-bit
+ * slices, W signed / K* unsigned bytes, n_train <= 8192, c0, c1 >= 0: 22 % fewer MMAs).  bk_gp_set_var_mode selects
+ * the sigma kernel: 0 = FP64 DMMA, 1 = int8 tensor cores + TMEM with scheme 0, 2 = with scheme 1 (the slices set with
+ * bk_gp_set_output_int8 must have been produced with the matching wq_scheme).  Results agree with mode 0 to ~1e-14 of
+ * the prior variance. */
 size_t bk_gp_wq_bytes(int n_train);
 int bk_gp_set_output_int8(bk_gp_t h, int q, const int8_t* wq_dev, const double* wsig_dev);
 int bk_gp_set_var_mode(bk_gp_t h, int mode);
@@ -106,12 +109,13 @@ int bk_lml_batched(const double* x_dev, const double* y_dev, int n_train, int p,
  * w_tiles_dev (bk_gp_wtiles_len doubles or NULL) = packed L^-1, lml_dev (1), info_dev (1; 0 = positive definite). */
 int bk_gp_factorise(const double* x_dev, const double* y_dev, int n_train, int p, int kind, double c0, double c1,
                     double kdiag, const double* ls_host, double* l_dev, double* alpha_dev, double* w_tiles_dev,
-                    int8_t* wq_dev /* or NULL */, double* wsig_dev /* or NULL */, double* lml_dev, int* info_dev,
-                    void* workspace_dev, size_t workspace_bytes, void* stream);
+                    int8_t* wq_dev /* or NULL */, double* wsig_dev /* or NULL */, int wq_scheme, double* lml_dev,
+                    int* info_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 /* Packed L^-1 tiles from a given Cholesky factor l_dev (n x n row-major lower), e.g. scikit-learn's L_;
  * workspace: bk_lml_workspace(n, 1, 1). */
 int bk_tri_inverse_pack(const double* l_dev, int n_train, double* w_tiles_dev, int8_t* wq_dev /* or NULL */,
-                        double* wsig_dev /* or NULL */, void* workspace_dev, size_t workspace_bytes, void* stream);
+                        double* wsig_dev /* or NULL */, int wq_scheme, void* workspace_dev, size_t workspace_bytes,
+                        void* stream);
 
 /* ---- Saltelli experiment + estimator: replaces ot.SobolIndicesExperiment(...).generate(),
  *      UQ.func over the design, and ot.SaltelliSensitivityAlgorithm (uq/uq.py:331-349,367-375) ---- */

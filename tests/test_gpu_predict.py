@@ -184,22 +184,26 @@ def test_fit_on_device_reproduces_docstring_and_sklearn_lml():
         assert sigma[0, q] == pytest.approx(rs[0], rel=1e-7)
 
 
+@pytest.mark.parametrize('scheme', [0, 1])
 @pytest.mark.parametrize('n,p,kind,ls', [(1024, 8, 'matern32', 3.0), (700, 5, 'matern52', 1.0), (100, 3, 'matern32', 0.7),
                                          (333, 3, 'rbf', 0.4)])
-def test_int8_tensor_core_sigma_matches_fp64_path(n, p, kind, ls):
-    """k_var_ozaki (tcgen05 int8, error-free slicing) against k_var_trmm (FP64 DMMA) and the long-double value."""
+def test_int8_tensor_core_sigma_matches_fp64_path(n, p, kind, ls, scheme):
+    """k_var_ozaki (tcgen05 int8, error-free slicing; scheme 0 = 8 x 7-bit, 1 = 7 x 8-bit with unsigned K* bytes)
+    against k_var_trmm (FP64 DMMA) and the long-double value."""
     st = synthetic_state(n, p, kind, ls=np.full(p, ls))
     k = kriging_from_states([st])
     rng = np.random.RandomState(5)
     pts = np.vstack([rng.rand(700, p), st['X_train'][:5]])
-    k._model().set_sigma_kernel('dmma')
+    model = k._model()
+    model.set_sigma_kernel('dmma')
     m0, s0 = k.evaluate(pts)
-    k._model().set_sigma_kernel('int8')
+    model.set_sigma_kernel('int8')
+    model.set_int8_scheme(scheme)
     m1, s1 = k.evaluate(pts)
     prior = ogp.kernel_diag(st['tree']) * st['y_std'] ** 2
     np.testing.assert_array_equal(m0, m1)
     err = np.max(np.abs(s1 ** 2 - s0 ** 2)) / prior
     _, sld = gp_hp.predict_hp(st, pts[:32])
     err_ld = np.max(np.abs(s1[:32, 0] ** 2 - (sld ** 2).astype(float))) / prior
-    print("n=%d %s: int8-vs-DMMA %.2e, int8-vs-longdouble %.2e (of the prior variance)" % (n, kind, err, err_ld))
+    print("n=%d %s scheme %d: int8-vs-DMMA %.2e, int8-vs-longdouble %.2e (of the prior variance)" % (n, kind, scheme, err, err_ld))
     assert err <= 1e-11 and err_ld <= RTOL

@@ -134,9 +134,10 @@ def measure_dgemm_peak(torch):
     return 2 * n ** 3 / best * 1e-12
 
 
-def ncu_traffic_bytes():
-    """DRAM bytes of one k_var_trmm launch from the committed ncu capture (None if the summary is absent)."""
-    path = os.path.join(ROOT, 'profiles', 'r01_ncu_v2', 'k_var_trmm_summary.csv')
+def ncu_traffic_bytes(int8=False):
+    """DRAM bytes of one launch of the dominant kernel from the committed ncu capture (None if the summary is absent)."""
+    path = os.path.join(ROOT, 'profiles', 'r01_ncu_v4', 'k_var_ozaki_summary.csv') if int8 else \
+        os.path.join(ROOT, 'profiles', 'r01_ncu_v2', 'k_var_trmm_summary.csv')
     scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
     try:
         total = 0.0
@@ -330,23 +331,25 @@ def main():
     peak = measure_dgemm_peak(torch)
     int8 = model.sigma_kernel == 'int8'
     n_panels = (N_TRAIN + 127) // 128
-    # executed int8 work of k_var_ozaki: 36 slice-pair MMAs (M128 N128 K32) per 32-wide k slab, 2 nP (nP+1) slabs per tile
-    int8_ops_per_row = 36 * 2.0 * 128 * 128 * 32 * 2 * n_panels * (n_panels + 1) / 128
+    # executed int8 work of k_var_ozaki: 28 (7x8-bit scheme) or 36 (8x7-bit) slice-pair MMAs (M128 N128 K32) per 32-wide
+    # k slab, 2 nP (nP+1) slabs per tile of 128 rows
+    pairs = 28 if getattr(model, 'int8_scheme', 0) == 1 else 36
+    int8_ops_per_row = pairs * 2.0 * 128 * 128 * 32 * 2 * n_panels * (n_panels + 1) / 128
     int8_tops = int8_ops_per_row * rows_per_launch / (var_ms / max(1, var_launches) * 1e-3) * 1e-12
     roofline = {"bound": "tensor",
-                "kernel": "k_var_ozaki (tcgen05 int8 + TMEM: FP64 product evaluated exactly from 8x7-bit slices)" if int8
+                "kernel": "k_var_ozaki (tcgen05 int8 + TMEM: FP64 product evaluated exactly from int8 slices)" if int8
                           else "k_var_trmm (FP64 DMMA)",
                 "achieved": achieved, "peak": peak,
-                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes() if not int8 else None,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_traffic_bytes(int8),
                 "note": ("frac > 1 is expected: achieved counts ALGORITHMIC FP64 flops (n^2 + 2n per prediction) while the "
-                         "kernel runs them as 36 int8 MMAs on the tcgen05 pipe; peak stays the measured FP64 (cuBLAS DGEMM) "
+                         "kernel runs them as 28 or 36 int8 MMAs per slab on the tcgen05 pipe; peak stays the measured FP64 (cuBLAS DGEMM) "
                          "rate so the number is comparable across rounds.  int8 pipe: see int8_tensor.") if int8 else None,
                 "int8_tensor": {"achieved_tops": int8_tops, "peak_tops_same_shape": 3249.0, "peak_tops_n256": 4572.0,
                                 "frac_same_shape": int8_tops / 3249.0,
                                 "peak_source": "profiles/r01_int8_umma_probe.jsonl (tcgen05.mma kind::i8, SMEM operands)"} if int8 else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_var_trmm launch (151552 points), "
-                                  "ncu --set full capture in profiles/r01_ncu_v2/k_var_trmm_summary.csv; algorithmic bytes "
-                                  "per launch = K* chunk + W = %.3e" % (151552 * N_TRAIN * 8 + N_TRAIN * N_TRAIN * 8),
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (151552 points) of the dominant "
+                                  "kernel, ncu --set full capture in profiles/r01_ncu_v4 (int8) or r01_ncu_v2 (dmma); "
+                                  "algorithmic bytes per launch = K* chunk + W = %.3e" % (151552 * N_TRAIN * 8 + N_TRAIN * N_TRAIN * 8),
                 "peak_source": "measured live: torch.matmul fp64 8192^3 best of 10 (cuBLAS DGEMM); MEASURED_PEAKS.json "
                                "has no FP64 entry; raw DMMA pipe rate 37.1 TFLOP/s in profiles/r01_fp64_peaks.jsonl",
                 "algorithmic_flops_per_prediction": algo_flops_per_pred,

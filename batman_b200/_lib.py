@@ -28,6 +28,9 @@ SIGNATURES = {
     'bk_gp_wtiles_len': (ctypes.c_size_t, [ctypes.c_int]),
     'bk_gp_set_output': (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double,
                                         ctypes.c_double, c_double_p, vp, vp, vp, ctypes.c_double, ctypes.c_double]),
+    'bk_gp_set_output_general': (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, c_int_p, c_double_p, ctypes.c_int,
+                                                c_double_p, c_int_p, ctypes.c_double, vp, vp, vp, ctypes.c_double,
+                                                ctypes.c_double]),
     'bk_gp_wq_bytes': (ctypes.c_size_t, [ctypes.c_int]),
     'bk_gp_set_output_int8': (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
     'bk_gp_set_var_mode': (ctypes.c_int, [vp, ctypes.c_int]),
@@ -41,6 +44,12 @@ SIGNATURES = {
     'bk_gp_factorise': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                        ctypes.c_double, ctypes.c_double, c_double_p, vp, vp, vp, vp, vp, ctypes.c_int,
                                        vp, vp, vp, ctypes.c_size_t, vp]),
+    'bk_lml_batched_general': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p,
+                                              ctypes.c_int, c_int_p, c_double_p, c_double_p, c_double_p, vp, vp,
+                                              ctypes.c_size_t, vp]),
+    'bk_gp_factorise_general': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, ctypes.c_int,
+                                               c_int_p, c_double_p, c_double_p, ctypes.c_double, vp, vp, vp, vp, vp,
+                                               ctypes.c_int, vp, vp, vp, ctypes.c_size_t, vp]),
     'bk_tri_inverse_pack': (ctypes.c_int, [vp, ctypes.c_int, vp, vp, vp, ctypes.c_int, vp, ctypes.c_size_t, vp]),
     'bk_sobol_nsums': (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     'bk_sobol_nslots': (ctypes.c_int, []),

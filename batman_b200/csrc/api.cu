@@ -69,6 +69,13 @@ int gp_factorise(const double* X, const double* y, int n, int p, int kind, doubl
                  const double* ls, double* L_out, double* alpha_out, double* wt_tiles_out, int8_t* wq_out,
                  double* wsig_out, int wq_scheme, double* lml_out, int* info_out, void* ws, size_t ws_bytes,
                  cudaStream_t st);
+int lml_batched_general(const double* X, const double* y, int n, int p, int R, int nf, const int* fkind, int nt,
+                        const int* texp, const double* tcoef, const double* fls, const double* kdiag, double* lml_out,
+                        void* ws, size_t ws_bytes, cudaStream_t st);
+int gp_factorise_general(const double* X, const double* y, int n, int p, int nf, const int* fkind, int nt,
+                         const int* texp, const double* tcoef, const double* fls, double kdiag, double* L_out,
+                         double* alpha_out, double* wt_tiles_out, int8_t* wq_out, double* wsig_out, int wq_scheme,
+                         double* lml_out, int* info_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, int8_t* wq_out, double* wsig_out, int wq_scheme,
                      void* ws, size_t ws_bytes, cudaStream_t st);
 int sobol_nsums_host(int p, int second);
@@ -154,7 +161,48 @@ int bk_gp_set_output(bk_gp_t h, int q, int kind, double c0, double c1, double kd
     if (!ls_host || !xs_dev || !alpha_dev) return set_error("bk_gp_set_output: NULL pointer");
     GpOutput& o = h->out[q];
     o.kind = kind; o.c0 = c0; o.c1 = c1; o.kdiag = kdiag; o.y_mean = y_mean; o.y_std = y_std;
+    o.kmax = fabs(c0) + fabs(c1);            // stationary factor <= 1
+    o.nonneg = c0 >= 0.0 && c1 >= 0.0;
     for (int c = 0; c < MAX_P; ++c) o.ls[c] = c < h->p ? ls_host[c] : 1.0;
+    o.xs = xs_dev; o.alpha = alpha_dev; o.wt = w_tiles_dev;
+    return 0;
+}
+
+// shared validation of a general tree description (set_output_general, lml_batched_general, factorise_general)
+static int check_general(const char* who, int nf, const int* fkind, int nt, const int* texp, int P) {
+    if (nf < 1 || nf > GEN_MAX_F) return set_error("%s: %d stationary leaves (supported: 1..%d)", who, nf, GEN_MAX_F);
+    if (nt < 1 || nt > GEN_MAX_T) return set_error("%s: %d product terms (supported: 1..%d)", who, nt, GEN_MAX_T);
+    if (nf * P > GEN_MAX_FP) return set_error("%s: %d leaves x padded dimension %d exceeds %d", who, nf, P, GEN_MAX_FP);
+    for (int f = 0; f < nf; ++f)
+        if (fkind[f] < BK_MATERN12 || fkind[f] > BK_MATERN_INF) return set_error("%s: leaf %d has unknown kind %d", who, f, fkind[f]);
+    for (int i = 0; i < nt * nf; ++i)
+        if (texp[i] < 0 || texp[i] > 4) return set_error("%s: exponent %d out of range [0, 4]", who, texp[i]);
+    return 0;
+}
+
+int bk_gp_set_output_general(bk_gp_t h, int q, int nf, const int* fkind_host, const double* fls_host, int nt,
+                             const double* tcoef_host, const int* texp_host, double kdiag, const double* xs_dev,
+                             const double* alpha_dev, const double* w_tiles_dev, double y_mean, double y_std) {
+    if (!h) return set_error("bk_gp_set_output_general: NULL handle");
+    if (q < 0 || q >= h->m) return set_error("bk_gp_set_output_general: output %d out of range [0, %d)", q, h->m);
+    if (!fkind_host || !fls_host || !tcoef_host || !texp_host || !xs_dev || !alpha_dev)
+        return set_error("bk_gp_set_output_general: NULL pointer");
+    if (int rc = check_general("bk_gp_set_output_general", nf, fkind_host, nt, texp_host, h->P)) return rc;
+    GpOutput& o = h->out[q];
+    o.kind = BK_GENERAL; o.c0 = 0.0; o.c1 = 0.0; o.kdiag = kdiag; o.y_mean = y_mean; o.y_std = y_std;
+    o.gen = GenSpec();
+    o.gen.nf = nf; o.gen.nt = nt;
+    o.kmax = 0.0; o.nonneg = true;
+    for (int f = 0; f < nf; ++f) {
+        o.gen.fkind[f] = fkind_host[f];
+        for (int c = 0; c < MAX_P; ++c) o.gls[f][c] = c < h->p ? fls_host[(size_t)f * h->p + c] : 1.0;
+    }
+    for (int t = 0; t < nt; ++t) {
+        o.gen.tcoef[t] = tcoef_host[t];
+        o.kmax += fabs(tcoef_host[t]);
+        if (tcoef_host[t] < 0.0) o.nonneg = false;
+        for (int f = 0; f < nf; ++f) o.gen.texp[t][f] = (unsigned char)texp_host[t * nf + f];
+    }
     o.xs = xs_dev; o.alpha = alpha_dev; o.wt = w_tiles_dev;
     return 0;
 }
@@ -207,8 +255,8 @@ int bk_gp_set_var_mode(bk_gp_t h, int mode) {
     if (mode == 2 && h->n_pad > 8192) return set_error("bk_gp_set_var_mode: 7x8-bit int32 accumulation is exact only for n_train <= 8192");
     if (mode == 2)
         for (int q = 0; q < h->m; ++q)
-            if (h->out[q].c0 < 0.0 || h->out[q].c1 < 0.0)
-                return set_error("bk_gp_set_var_mode: the 7x8-bit scheme slices K* into unsigned bytes and needs c0, c1 >= 0");
+            if (!h->out[q].nonneg)
+                return set_error("bk_gp_set_var_mode: the 7x8-bit scheme slices K* into unsigned bytes and needs non-negative coefficients");
     h->var_mode = mode;
     return 0;
 }
@@ -241,7 +289,7 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
         for (int q = 0; q < h->m; ++q) {
             if (h->var_mode >= 1) {
                 const GpOutput& o = h->out[q];
-                const double kappa = pow2_at_least(fabs(o.c0) + fabs(o.c1));   // |k| <= |c0| + |c1| < kappa (stationary factor <= 1)
+                const double kappa = pow2_at_least(o.kmax);   // |k| <= |c0| + |c1| (or sum |coef_t|) < kappa
                 const int scheme = h->var_mode - 1;
                 if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, nullptr, (int8_t*)kstar,
                                             scheme, kappa, st)) return rc;
@@ -278,6 +326,34 @@ int bk_gp_factorise(const double* x_dev, const double* y_dev, int n_train, int p
         return set_error("bk_gp_factorise: NULL pointer");
     return gp_factorise(x_dev, y_dev, n_train, p, kind, c0, c1, kdiag, ls_host, l_dev, alpha_dev, w_tiles_dev, wq_dev,
                         wsig_dev, wq_scheme, lml_dev, info_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bk_lml_batched_general(const double* x_dev, const double* y_dev, int n_train, int p, int n_candidates, int nf,
+                           const int* fkind_host, int nt, const int* texp_host, const double* tcoef_host,
+                           const double* fls_host, const double* kdiag_host, double* lml_dev, void* workspace_dev,
+                           size_t workspace_bytes, void* stream) {
+    if (!x_dev || !y_dev || !fkind_host || !texp_host || !tcoef_host || !fls_host || !kdiag_host || !lml_dev || !workspace_dev)
+        return set_error("bk_lml_batched_general: NULL pointer");
+    if (n_train < 1 || p < 1 || n_candidates < 1) return set_error("bk_lml_batched_general: n, p, R must be >= 1");
+    if (padded_dim(p) < 0) return set_error("bk_lml_batched_general: input dimension %d > %d", p, MAX_P);
+    if (int rc = check_general("bk_lml_batched_general", nf, fkind_host, nt, texp_host, padded_dim(p))) return rc;
+    return lml_batched_general(x_dev, y_dev, n_train, p, n_candidates, nf, fkind_host, nt, texp_host, tcoef_host,
+                               fls_host, kdiag_host, lml_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+}
+
+int bk_gp_factorise_general(const double* x_dev, const double* y_dev, int n_train, int p, int nf,
+                            const int* fkind_host, int nt, const int* texp_host, const double* tcoef_host,
+                            const double* fls_host, double kdiag, double* l_dev, double* alpha_dev, double* w_tiles_dev,
+                            int8_t* wq_dev, double* wsig_dev, int wq_scheme, double* lml_dev, int* info_dev,
+                            void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!x_dev || !y_dev || !fkind_host || !texp_host || !tcoef_host || !fls_host || !l_dev || !alpha_dev || !lml_dev ||
+        !info_dev || !workspace_dev)
+        return set_error("bk_gp_factorise_general: NULL pointer");
+    if (padded_dim(p) < 0) return set_error("bk_gp_factorise_general: input dimension %d > %d", p, MAX_P);
+    if (int rc = check_general("bk_gp_factorise_general", nf, fkind_host, nt, texp_host, padded_dim(p))) return rc;
+    return gp_factorise_general(x_dev, y_dev, n_train, p, nf, fkind_host, nt, texp_host, tcoef_host, fls_host, kdiag,
+                                l_dev, alpha_dev, w_tiles_dev, wq_dev, wsig_dev, wq_scheme, lml_dev, info_dev,
+                                workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }
 
 int bk_tri_inverse_pack(const double* l_dev, int n_train, double* w_tiles_dev, int8_t* wq_dev, double* wsig_dev,

@@ -35,6 +35,8 @@ struct Cand {
     int pad_;
     double c0, c1, kdiag;
     double ls[MAX_P];
+    GenSpec gen;                      // kind == BK_GENERAL
+    double gls[GEN_MAX_F][MAX_P];
 };
 
 // ---------------------------------------------------------------- K(theta_r): lower block tiles
@@ -42,22 +44,24 @@ __global__ void __launch_bounds__(256) k_build_K(const double* __restrict__ X, i
                                                  const Cand* __restrict__ cands, double* __restrict__ M,
                                                  long batch_stride) {
     extern __shared__ __align__(16) double sm[];
-    double* xr = sm;                 // [128][p]   rows of this tile, scaled
-    double* xcT = sm + NB * p;       // [p][128]   cols of this tile, scaled, transposed
     // lower-triangular tile index -> (bi, bj), bj <= bi
     int t = blockIdx.x, bi = 0;
     while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
     const int bj = t - bi * (bi + 1) / 2;
     const Cand& cd = cands[blockIdx.y];
     double* Mr = M + (size_t)blockIdx.y * batch_stride;
-    for (int idx = threadIdx.x; idx < NB * p; idx += blockDim.x) {
-        const int r = idx / p, c = idx % p;
+    const int kind = cd.kind;
+    const int nf = kind == BK_GENERAL ? cd.gen.nf : 1;
+    double* xr = sm;                      // [nf][128][p]   rows of this tile, scaled per leaf
+    double* xcT = sm + nf * NB * p;       // [nf][p][128]   cols of this tile, scaled, transposed
+    for (int idx = threadIdx.x; idx < nf * NB * p; idx += blockDim.x) {
+        const int f = idx / (NB * p), r = (idx / p) % NB, c = idx % p;
         const int gr = bi * NB + r, gc = bj * NB + r;
-        xr[r * p + c] = gr < n ? __ddiv_rn(X[(size_t)gr * p + c], cd.ls[c]) : 0.0;     // X / length_scale
-        xcT[c * NB + r] = gc < n ? __ddiv_rn(X[(size_t)gc * p + c], cd.ls[c]) : 0.0;
+        const double l = kind == BK_GENERAL ? cd.gls[f][c] : cd.ls[c];
+        xr[(f * NB + r) * p + c] = gr < n ? __ddiv_rn(X[(size_t)gr * p + c], l) : 0.0;     // X / length_scale
+        xcT[(f * p + c) * NB + r] = gc < n ? __ddiv_rn(X[(size_t)gc * p + c], l) : 0.0;
     }
     __syncthreads();
-    const int kind = cd.kind;
     for (int e = 0; e < NB * NB / 256; ++e) {
         const int idx = e * 256 + threadIdx.x;
         const int r = idx >> 7, c = idx & 127;
@@ -68,20 +72,17 @@ __global__ void __launch_bounds__(256) k_build_K(const double* __restrict__ X, i
         } else if (gr == gc) {
             v = __dadd_rn(cd.kdiag, JITTER);                            // kernel_.diag + alpha (sklearn:_gpr.py:589)
         } else {
-            double s = 0.0;
-            for (int d = 0; d < p; ++d) {                               // pdist order: sequential, non-fused
-                const double df = __dadd_rn(xr[r * p + d], -xcT[d * NB + c]);
-                s = __dadd_rn(s, __dmul_rn(df, df));
+            double fv[GEN_MAX_F] = {1.0, 1.0, 1.0};
+            for (int f = 0; f < nf; ++f) {
+                double s = 0.0;
+                for (int d = 0; d < p; ++d) {                           // pdist order: sequential, non-fused
+                    const double df = __dadd_rn(xr[(f * NB + r) * p + d], -xcT[(f * p + d) * NB + c]);
+                    s = __dadd_rn(s, __dmul_rn(df, df));
+                }
+                const double val = stationary_rt(kind == BK_GENERAL ? cd.gen.fkind[f] : kind, s);
+                if (f == 0) fv[0] = val; else if (f == 1) fv[1] = val; else fv[2] = val;
             }
-            double f;
-            switch (kind) {
-                case BK_MATERN12: f = stationary<BK_MATERN12>(s); break;
-                case BK_MATERN32: f = stationary<BK_MATERN32>(s); break;
-                case BK_MATERN52: f = stationary<BK_MATERN52>(s); break;
-                case BK_RBF: f = stationary<BK_RBF>(s); break;
-                default: f = stationary<BK_MATERN_INF>(s); break;
-            }
-            v = affine(cd.c0, cd.c1, f);
+            v = kind == BK_GENERAL ? general_cov(cd.gen, fv) : affine(cd.c0, cd.c1, fv[0]);
         }
         Mr[(size_t)gr * n_pad + gc] = v;
     }
@@ -366,16 +367,39 @@ static LmlWorkspace carve(void* ws, int n, int R, double** wt_out) {
     return w;
 }
 
-static int upload_cands(const LmlWorkspace& w, int R, int p, const int* kinds, const double* c0, const double* c1,
-                        const double* kdiag, const double* ls, cudaStream_t st) {
-    std::vector<Cand> h(R);
+static int upload_cands(const LmlWorkspace& w, const std::vector<Cand>& h, cudaStream_t st) {
+    BK_CUDA(cudaMemcpyAsync(w.cands, h.data(), sizeof(Cand) * h.size(), cudaMemcpyHostToDevice, st));
+    BK_CUDA(cudaStreamSynchronize(st));     // h belongs to the caller's frame
+    return 0;
+}
+static int affine_cands(std::vector<Cand>& h, int R, int p, const int* kinds, const double* c0, const double* c1,
+                        const double* kdiag, const double* ls) {
+    h.assign(R, Cand());
     for (int r = 0; r < R; ++r) {
         if (kinds[r] < BK_MATERN12 || kinds[r] > BK_MATERN_INF) return set_error("candidate %d: unknown kernel kind %d", r, kinds[r]);
         h[r].kind = kinds[r]; h[r].pad_ = 0; h[r].c0 = c0[r]; h[r].c1 = c1[r]; h[r].kdiag = kdiag[r];
         for (int c = 0; c < MAX_P; ++c) h[r].ls[c] = c < p ? ls[(size_t)r * p + c] : 1.0;
     }
-    BK_CUDA(cudaMemcpyAsync(w.cands, h.data(), sizeof(Cand) * R, cudaMemcpyHostToDevice, st));
-    BK_CUDA(cudaStreamSynchronize(st));     // h goes out of scope
+    return 0;
+}
+// general trees: one shape (nf, fkind, nt, texp) for all candidates; tcoef R x nt, fls R x nf x p, kdiag R
+static int general_cands(std::vector<Cand>& h, int R, int p, int nf, const int* fkind, int nt, const int* texp,
+                         const double* tcoef, const double* fls, const double* kdiag) {
+    h.assign(R, Cand());
+    for (int r = 0; r < R; ++r) {
+        Cand& cd = h[r];
+        cd.kind = BK_GENERAL; cd.pad_ = 0; cd.c0 = 0.0; cd.c1 = 0.0; cd.kdiag = kdiag[r];
+        for (int c = 0; c < MAX_P; ++c) cd.ls[c] = 1.0;
+        cd.gen.nf = nf; cd.gen.nt = nt;
+        for (int f = 0; f < nf; ++f) {
+            cd.gen.fkind[f] = fkind[f];
+            for (int c = 0; c < MAX_P; ++c) cd.gls[f][c] = c < p ? fls[((size_t)r * nf + f) * p + c] : 1.0;
+        }
+        for (int t = 0; t < nt; ++t) {
+            cd.gen.tcoef[t] = tcoef[(size_t)r * nt + t];
+            for (int f = 0; f < nf; ++f) cd.gen.texp[t][f] = (unsigned char)texp[t * nf + f];
+        }
+    }
     return 0;
 }
 
@@ -440,9 +464,9 @@ static int trtri_sweep(const double* M, const double* Winv, double* WT, int n, c
 int launch_pack_w_ex(const double* w, int n_rows_valid, int ld, int transposed, double* out, cudaStream_t st);
 int launch_slice_w(const double* src, int n, int ld, int transposed, int scheme, int8_t* wq, double* wsig, cudaStream_t st);
 
-static int build_K(const LmlWorkspace& w, const double* X, int n, int p, int R, cudaStream_t st) {
+static int build_K(const LmlWorkspace& w, const double* X, int n, int p, int R, int nf, cudaStream_t st) {
     const int n_pad = padded_n(n), nP = n_pad / NB;
-    const size_t smem = (size_t)2 * NB * p * 8;
+    const size_t smem = (size_t)2 * nf * NB * p * 8;
     if (smem > 48 * 1024) BK_CUDA(cudaFuncSetAttribute(k_build_K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope prof(PROF_CHOL, st);
     k_build_K<<<dim3(nP * (nP + 1) / 2, R), 256, smem, st>>>(X, n, p, n_pad, w.cands, w.M, (long)n_pad * n_pad);
@@ -457,36 +481,51 @@ static int stage_y(const LmlWorkspace& w, const double* y, int n, cudaStream_t s
     return 0;
 }
 
-int lml_batched(const double* X, const double* y, int n, int p, int R, const int* kinds, const double* c0,
-                const double* c1, const double* kdiag, const double* ls, double* lml_out, void* ws, size_t ws_bytes,
-                cudaStream_t st) {
+static int lml_cands(const double* X, const double* y, int n, int p, const std::vector<Cand>& cands, int nf,
+                     double* lml_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int R = (int)cands.size();
     if (p > MAX_P) return set_error("p = %d exceeds %d", p, MAX_P);
     if (ws_bytes < lml_workspace_bytes(n, R, false))
         return set_error("bk_lml_batched: workspace of %zu bytes needed (got %zu)", lml_workspace_bytes(n, R, false), ws_bytes);
     LmlWorkspace w = carve(ws, n, R, nullptr);
-    if (int rc = upload_cands(w, R, p, kinds, c0, c1, kdiag, ls, st)) return rc;
+    if (int rc = upload_cands(w, cands, st)) return rc;
     if (int rc = stage_y(w, y, n, st)) return rc;
-    if (int rc = build_K(w, X, n, p, R, st)) return rc;
+    if (int rc = build_K(w, X, n, p, R, nf, st)) return rc;
     if (int rc = cholesky_sweep(w, n, R, nullptr, st)) return rc;
     k_lml_final<<<(R + 127) / 128, 128, 0, st>>>(w.acc, w.info, n, R, lml_out);
     BK_LAUNCH_CHECK("k_lml_final");
     return 0;
 }
 
+int lml_batched(const double* X, const double* y, int n, int p, int R, const int* kinds, const double* c0,
+                const double* c1, const double* kdiag, const double* ls, double* lml_out, void* ws, size_t ws_bytes,
+                cudaStream_t st) {
+    std::vector<Cand> cands;
+    if (int rc = affine_cands(cands, R, p, kinds, c0, c1, kdiag, ls)) return rc;
+    return lml_cands(X, y, n, p, cands, 1, lml_out, ws, ws_bytes, st);
+}
+
+int lml_batched_general(const double* X, const double* y, int n, int p, int R, int nf, const int* fkind, int nt,
+                        const int* texp, const double* tcoef, const double* fls, const double* kdiag, double* lml_out,
+                        void* ws, size_t ws_bytes, cudaStream_t st) {
+    std::vector<Cand> cands;
+    if (int rc = general_cands(cands, R, p, nf, fkind, nt, texp, tcoef, fls, kdiag)) return rc;
+    return lml_cands(X, y, n, p, cands, nf, lml_out, ws, ws_bytes, st);
+}
+
 // final state at the chosen theta: L (n_pad x n_pad, row-major lower), alpha (n_pad), packed W tiles, lml, info
-int gp_factorise(const double* X, const double* y, int n, int p, int kind, double c0, double c1, double kdiag,
-                 const double* ls, double* L_out, double* alpha_out, double* wt_tiles_out, int8_t* wq_out,
-                 double* wsig_out, int wq_scheme, double* lml_out, int* info_out, void* ws, size_t ws_bytes,
-                 cudaStream_t st) {
+static int factorise_cand(const double* X, const double* y, int n, int p, const std::vector<Cand>& cand, int nf,
+                          double* L_out, double* alpha_out, double* wt_tiles_out, int8_t* wq_out, double* wsig_out,
+                          int wq_scheme, double* lml_out, int* info_out, void* ws, size_t ws_bytes, cudaStream_t st) {
     if (p > MAX_P) return set_error("p = %d exceeds %d", p, MAX_P);
     if (ws_bytes < lml_workspace_bytes(n, 1, true))
         return set_error("bk_gp_factorise: workspace of %zu bytes needed (got %zu)", lml_workspace_bytes(n, 1, true), ws_bytes);
     const int n_pad = padded_n(n);
     double* WT = nullptr;
     LmlWorkspace w = carve(ws, n, 1, &WT);
-    if (int rc = upload_cands(w, 1, p, &kind, &c0, &c1, &kdiag, ls, st)) return rc;
+    if (int rc = upload_cands(w, cand, st)) return rc;
     if (int rc = stage_y(w, y, n, st)) return rc;
-    if (int rc = build_K(w, X, n, p, 1, st)) return rc;
+    if (int rc = build_K(w, X, n, p, 1, nf, st)) return rc;
     BK_CUDA(cudaMemsetAsync(WT, 0, sizeof(double) * n_pad * n_pad, st));
     if (int rc = cholesky_sweep(w, n, 1, WT, st)) return rc;
     k_lml_final<<<1, 128, 0, st>>>(w.acc, w.info, n, 1, lml_out);
@@ -501,6 +540,26 @@ int gp_factorise(const double* X, const double* y, int n, int p, int kind, doubl
     if (wq_out && wsig_out)
         if (int rc = launch_slice_w(WT, n, n_pad, 1, wq_scheme, wq_out, wsig_out, st)) return rc;
     return 0;
+}
+
+int gp_factorise(const double* X, const double* y, int n, int p, int kind, double c0, double c1, double kdiag,
+                 const double* ls, double* L_out, double* alpha_out, double* wt_tiles_out, int8_t* wq_out,
+                 double* wsig_out, int wq_scheme, double* lml_out, int* info_out, void* ws, size_t ws_bytes,
+                 cudaStream_t st) {
+    std::vector<Cand> cand;
+    if (int rc = affine_cands(cand, 1, p, &kind, &c0, &c1, &kdiag, ls)) return rc;
+    return factorise_cand(X, y, n, p, cand, 1, L_out, alpha_out, wt_tiles_out, wq_out, wsig_out, wq_scheme, lml_out,
+                          info_out, ws, ws_bytes, st);
+}
+
+int gp_factorise_general(const double* X, const double* y, int n, int p, int nf, const int* fkind, int nt,
+                         const int* texp, const double* tcoef, const double* fls, double kdiag, double* L_out,
+                         double* alpha_out, double* wt_tiles_out, int8_t* wq_out, double* wsig_out, int wq_scheme,
+                         double* lml_out, int* info_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    std::vector<Cand> cand;
+    if (int rc = general_cands(cand, 1, p, nf, fkind, nt, texp, tcoef, fls, &kdiag)) return rc;
+    return factorise_cand(X, y, n, p, cand, nf, L_out, alpha_out, wt_tiles_out, wq_out, wsig_out, wq_scheme, lml_out,
+                          info_out, ws, ws_bytes, st);
 }
 
 // W tiles from a given Cholesky factor (models adopted from scikit-learn state)

@@ -6,6 +6,7 @@
 #pragma once
 #include "../../include/batman_b200.h"
 #include "fastmath.cuh"
+#include "model.h"
 
 namespace bk {
 
@@ -34,6 +35,36 @@ __device__ __forceinline__ double stationary(double s) {
 // k = c0 + c1 * f : ConstantKernel * stat (c0 = 0), stat alone (c1 = 1), ConstantKernel + stat (c1 = 1)
 __device__ __forceinline__ double affine(double c0, double c1, double f) {
     return __dadd_rn(c0, __dmul_rn(c1, f));
+}
+
+// runtime kind (warp-uniform branch): the general kernels and the training-covariance builder
+__device__ __forceinline__ double stationary_rt(int kind, double s) {
+    switch (kind) {
+        case BK_MATERN12: return stationary<BK_MATERN12>(s);
+        case BK_MATERN32: return stationary<BK_MATERN32>(s);
+        case BK_MATERN52: return stationary<BK_MATERN52>(s);
+        case BK_RBF: return stationary<BK_RBF>(s);
+        default: return stationary<BK_MATERN_INF>(s);
+    }
+}
+
+// k = sum_t coef_t * prod_f fv[f]^texp[t][f]: Sum adds, Product multiplies, every operation rounded like the numpy
+// expression of the tree evaluated left to right (sklearn:kernels.py:870, 968).  A term starts from its first
+// operand -- 1.0 * f is exact, so a unit coefficient costs no rounding either way.
+__device__ __forceinline__ double general_cov(const GenSpec& g, const double (&fv)[GEN_MAX_F]) {
+    double k = 0.0;
+#pragma unroll
+    for (int t = 0; t < GEN_MAX_T; ++t) {
+        if (t < g.nt) {
+            double term = g.tcoef[t];
+#pragma unroll
+            for (int f = 0; f < GEN_MAX_F; ++f)
+                if (f < g.nf)
+                    for (int e = 0; e < g.texp[t][f]; ++e) term = __dmul_rn(term, fv[f]);
+            k = t == 0 ? term : __dadd_rn(k, term);
+        }
+    }
+    return k;
 }
 
 }  // namespace bk

@@ -14,6 +14,7 @@
 // negligible (8P/256 B of training data per pair from L2).
 #include "common.cuh"
 #include "covariance.cuh"
+#include "kstar_writers.cuh"
 #include "model.h"
 
 namespace bk {
@@ -87,25 +88,13 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(const PredictParams<P>
 #pragma unroll
     for (int e = 0; e < PRED_TP; ++e) { acc[e] = 0.0; comp[e] = 0.0; }
 
-    // K* destination of this thread (see gp_var.cu for the tile layout)
+    // K* destination of this thread (see gp_var.cu / var_ozaki.cu for the tile layouts)
     double* kdst[PRED_TP];
     int8_t* qdst[PRED_TP];
-    if constexpr (WRITE_K >= 2) {
 #pragma unroll
-        for (int e = 0; e < PRED_TP; ++e) {
-            const long t = t_idx[e];
-            const int r = (int)(t % TILE_T);
-            qdst[e] = prm.kq + (size_t)(t / TILE_T) * (prm.n_pad / 32) * 8 * 4096 + (r >> 3) * 256 + (r & 7) * 16;
-        }
-    }
-    if constexpr (WRITE_K == 1) {
-#pragma unroll
-        for (int e = 0; e < PRED_TP; ++e) {
-            long t = t_idx[e];
-            long T = t / TILE_T;
-            int tl = (int)(t % TILE_T);
-            kdst[e] = prm.kstar + (size_t)T * (prm.n_pad / TILE_K) * TILE_DOUBLES + (tl / 8) * 128 + (tl % 8) * 8;
-        }
+    for (int e = 0; e < PRED_TP; ++e) {
+        kdst[e] = WRITE_K == 1 ? kstar_tile_base(prm.kstar, t_idx[e], prm.n_pad) : nullptr;
+        qdst[e] = WRITE_K >= 2 ? kq_tile_base(prm.kq, t_idx[e], prm.n_pad) : nullptr;
     }
 
     for (int tile = 0; tile < ntiles; ++tile) {
@@ -144,87 +133,10 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(const PredictParams<P>
                     acc[e] = tsum;
                 }
             }
-            if constexpr (WRITE_K == 2) {
-                // error-free int8 slicing: k / kappa = sum_a q_a 2^-(7a-1), |q_a| <= 64 (var_ozaki.cu)
-                const int jg = tile * PRED_TJ + j8;
-#pragma unroll
-                for (int e = 0; e < PRED_TP; ++e) {
-                    unsigned int pk[8][2];
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) pk[a][0] = pk[a][1] = 0u;
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        // X = rint(k/kappa * 2^55) = hi * 2^28 + lo from two magic-number roundings (no F2I), then
-                        // signed base-128 digits in [-64, 63] with 32-bit integer ops: X = sum_a q_a 2^(56-7a)
-                        const double x27 = __dmul_rn(__dmul_rn(kbuf[e][jj], prm.inv_kappa), 0x1p27);
-                        const double hm = __dadd_rn(x27, 6755399441055744.0);
-                        int hi = __double2loint(hm);                                  // rint(x * 2^27), |hi| <= 2^27
-                        const double r28 = __dmul_rn(__dadd_rn(x27, -__dadd_rn(hm, -6755399441055744.0)), 0x1p28);
-                        int lo = __double2loint(__dadd_rn(r28, 6755399441055744.0));  // |lo| <= 2^27
-                        const int sh = 8 * (jj & 3), w = jj >> 2;
-#pragma unroll
-                        for (int a = 7; a >= 4; --a) {                                // slices 8..5 from lo
-                            const int dgt = ((lo + 64) & 127) - 64;
-                            pk[a][w] |= (unsigned int)(dgt & 255) << sh;
-                            lo = (lo - dgt) >> 7;
-                        }
-                        hi += lo;                                                     // carry out of the low half
-#pragma unroll
-                        for (int a = 3; a >= 1; --a) {                                // slices 4..2 from hi
-                            const int dgt = ((hi + 64) & 127) - 64;
-                            pk[a][w] |= (unsigned int)(dgt & 255) << sh;
-                            hi = (hi - dgt) >> 7;
-                        }
-                        pk[0][w] |= (unsigned int)(hi & 255) << sh;                   // slice 1: |hi| <= 64
-                    }
-                    int8_t* d = qdst[e] + (size_t)(jg >> 5) * 8 * 4096 + ((jg & 31) >> 4) * 128 + (jg & 15);
-#pragma unroll
-                    for (int a = 0; a < 8; ++a) *reinterpret_cast<uint2*>(d + (size_t)a * 4096) = make_uint2(pk[a][0], pk[a][1]);
-                }
-            }
-            if constexpr (WRITE_K == 3) {
-                // unsigned byte slicing: X = rint(k/kappa * 2^56) in [0, 2^56) = hi * 2^28 + lo; slice b = byte 7-b of X
-                const int jg = tile * PRED_TJ + j8;
-#pragma unroll
-                for (int e = 0; e < PRED_TP; ++e) {
-                    unsigned int pk[7][2];
-#pragma unroll
-                    for (int a = 0; a < 7; ++a) pk[a][0] = pk[a][1] = 0u;
-#pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const double x28 = __dmul_rn(__dmul_rn(kbuf[e][jj], prm.inv_kappa), 0x1p28);
-                        const double hm = __dadd_rn(x28, 6755399441055744.0);
-                        int hi = __double2loint(hm);                                  // rint(x * 2^28) in [0, 2^28]
-                        const double r28 = __dmul_rn(__dadd_rn(x28, -__dadd_rn(hm, -6755399441055744.0)), 0x1p28);
-                        int lo = __double2loint(__dadd_rn(r28, 6755399441055744.0));  // in [-2^27, 2^27]
-                        if (lo < 0) { lo += 1 << 28; hi -= 1; }                       // 0 <= lo < 2^28
-                        if (hi < 0) { hi = 0; lo = 0; }                               // k slightly below 0 by rounding: clamp
-                        const unsigned int uh = (unsigned int)hi, ul = (unsigned int)lo;
-                        const int sh = 8 * (jj & 3), w = jj >> 2;
-                        pk[0][w] |= ((uh >> 20) & 255u) << sh;                        // bits 48..55
-                        pk[1][w] |= ((uh >> 12) & 255u) << sh;
-                        pk[2][w] |= ((uh >> 4) & 255u) << sh;
-                        pk[3][w] |= ((((uh & 15u) << 4) | (ul >> 24)) & 255u) << sh;   // bits 24..31
-                        pk[4][w] |= ((ul >> 16) & 255u) << sh;
-                        pk[5][w] |= ((ul >> 8) & 255u) << sh;
-                        pk[6][w] |= (ul & 255u) << sh;                                // bits 0..7
-                    }
-                    int8_t* d = qdst[e] + (size_t)(jg >> 5) * 8 * 4096 + ((jg & 31) >> 4) * 128 + (jg & 15);
-#pragma unroll
-                    for (int a = 0; a < 7; ++a) *reinterpret_cast<uint2*>(d + (size_t)a * 4096) = make_uint2(pk[a][0], pk[a][1]);
-                }
-            }
-            if constexpr (WRITE_K == 1) {
+            if constexpr (WRITE_K != 0) {
                 const int jg = tile * PRED_TJ + j8;          // global train index of kbuf[.][0]
 #pragma unroll
-                for (int e = 0; e < PRED_TP; ++e) {
-                    double* d = kdst[e] + (size_t)(jg / TILE_K) * TILE_DOUBLES + ((jg % TILE_K) / 8) * 64;
-                    // lane order inside an 8-wide k group: (tq, h) -> j = tq + 4h
-                    reinterpret_cast<double2*>(d)[0] = make_double2(kbuf[e][0], kbuf[e][4]);
-                    reinterpret_cast<double2*>(d)[1] = make_double2(kbuf[e][1], kbuf[e][5]);
-                    reinterpret_cast<double2*>(d)[2] = make_double2(kbuf[e][2], kbuf[e][6]);
-                    reinterpret_cast<double2*>(d)[3] = make_double2(kbuf[e][3], kbuf[e][7]);
-                }
+                for (int e = 0; e < PRED_TP; ++e) kstar_write8<WRITE_K>(kbuf[e], jg, kdst[e], qdst[e], prm.inv_kappa);
             }
         }
         __syncthreads();   // everyone is done reading stage s
@@ -313,6 +225,9 @@ int launch_debug_fastmath(const double* in, long n, double* o_sqrt, double* o_ex
     return 0;
 }
 
+int launch_predict_general(const bk_gp_s* h, int q, const double* pts, long k, double* mean, int ld, int col,
+                           double* kstar, int8_t* kq, int kq_scheme, double kappa, cudaStream_t st);   // gp_predict_gen.cu
+
 // mean of output q at k points; if kstar != null also the packed K* tiles for gp_var
 int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar, int8_t* kq,
                    int kq_scheme, double kappa, cudaStream_t st) {
@@ -322,6 +237,7 @@ int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* m
         case BK_MATERN52: return launch_predict_k<BK_MATERN52>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
         case BK_RBF: return launch_predict_k<BK_RBF>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
         case BK_MATERN_INF: return launch_predict_k<BK_MATERN_INF>(h, q, pts, k, mean, kstar, kq, kq_scheme, kappa, st);
+        case BK_GENERAL: return launch_predict_general(h, q, pts, k, mean, h->m, q, kstar, kq, kq_scheme, kappa, st);
     }
     return set_error("output %d has no kernel set", q);
 }

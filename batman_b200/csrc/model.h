@@ -14,8 +14,24 @@ constexpr int TILE_M = 128;      // rows of W per DMMA row panel
 constexpr int TILE_K = 16;       // train points per staged K slab
 constexpr int TILE_DOUBLES = TILE_M * TILE_K;   // 2048 doubles = 16 KiB per packed tile
 
+// General covariance (kind == BK_GENERAL): k = sum_t coef_t * prod_f stat_{fkind[f]}(||(x - x')/ls_f||)^texp[t][f],
+// the expanded form of a Sum/Product tree over Constant/White/RBF/Matern leaves (kernel_spec.py).
+constexpr int GEN_MAX_F = 3;     // stationary leaves
+constexpr int GEN_MAX_T = 6;     // product terms
+constexpr int GEN_MAX_FP = 48;   // nf * P that fits the staging buffers of the general kernels
+struct GenSpec {
+    int nf = 0, nt = 0;
+    int fkind[GEN_MAX_F] = {0, 0, 0};
+    double tcoef[GEN_MAX_T] = {0, 0, 0, 0, 0, 0};
+    unsigned char texp[GEN_MAX_T][GEN_MAX_F] = {};
+};
+
 struct GpOutput {
     int kind = -1;
+    GenSpec gen;                     // kind == BK_GENERAL: xs is n_pad x (nf * P), factor-major inside a row
+    double gls[GEN_MAX_F][MAX_P];    //   length scales of the factors
+    double kmax = 1;                 // bound on |k(x, x')|: |c0| + |c1|, or sum |coef_t|
+    bool nonneg = true;              // every coefficient >= 0 (K* can be sliced into unsigned bytes)
     double c0 = 0, c1 = 1, kdiag = 1, y_mean = 0, y_std = 1;
     double ls[MAX_P];
     const double* xs = nullptr;      // n_pad x P   (X_train / ls, zero padded)

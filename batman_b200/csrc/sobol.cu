@@ -198,6 +198,10 @@ static int launch_sobol_k(const bk_gp_s* h, int q, const double* a, const double
     return set_error("unsupported padded dimension %d", h->P);
 }
 
+static int launch_sobol_general(const bk_gp_s* h, int q, const double* a, const double* b, uint64_t seed,
+                                const int* mkind, const double* mpar, long row_lo, long count, int second,
+                                double shift, double* partials, double* yout, cudaStream_t st);
+
 int launch_sobol(const bk_gp_s* h, int q, const double* a, const double* b, uint64_t seed, const int* mkind,
                  const double* mpar, long row_lo, long count, int second, double shift, double* partials,
                  double* yout, cudaStream_t st) {
@@ -207,6 +211,7 @@ int launch_sobol(const bk_gp_s* h, int q, const double* a, const double* b, uint
         case BK_MATERN52: return launch_sobol_k<BK_MATERN52>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, yout, st);
         case BK_RBF: return launch_sobol_k<BK_RBF>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, yout, st);
         case BK_MATERN_INF: return launch_sobol_k<BK_MATERN_INF>(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, yout, st);
+        case BK_GENERAL: return launch_sobol_general(h, q, a, b, seed, mkind, mpar, row_lo, count, second, shift, partials, yout, st);
     }
     return set_error("output %d has no kernel set", q);
 }
@@ -231,7 +236,7 @@ int launch_design_rows(uint64_t seed, long row_lo, long count, int p, const int*
 // (uq/uq.py:336-339).  HBM-bound: every y is read exactly once.  Warp w of the CTA walks base rows
 // k = w, w+nw, ...; lane = feature (coalesced 256 B per block row); accumulators live in shared memory.
 __global__ void k_sobol_y(const double* __restrict__ y, long ld_block, long count, int p, int F, int second, int nb,
-                          int nsums, const double* __restrict__ shift, double* __restrict__ partials) {
+                          int nsums, const double* __restrict__ shift, double* __restrict__ partials, long slot_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double* acc = reinterpret_cast<double*>(smem_raw);   // [nwarps][32][nsums][2]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -272,7 +277,7 @@ __global__ void k_sobol_y(const double* __restrict__ y, long ld_block, long coun
     __syncthreads();
     // combine the warps (fixed order) and ADD into slot kslot of feature f
     if (warp == 0 && f < F && kslot < nkslots) {
-        double* slot = partials + ((size_t)kslot * F + f) * nsums * 2;
+        double* slot = partials + (size_t)kslot * slot_stride + (size_t)f * nsums * 2;
         for (int r = 0; r < nsums; ++r) {
             dd t{slot[2 * r], slot[2 * r + 1]};
             for (int w = 0; w < nw; ++w) {
@@ -284,8 +289,9 @@ __global__ void k_sobol_y(const double* __restrict__ y, long ld_block, long coun
     }
 }
 
-int launch_sobol_y(const double* y, long ld_block, long count, int p, int F, int second, const double* shift,
-                   double* partials, cudaStream_t st) {
+// slot_stride: doubles between consecutive partial slots (0 = dense [slot][F][nsums][2])
+int launch_sobol_y_ex(const double* y, long ld_block, long count, int p, int F, int second, const double* shift,
+                      double* partials, long slot_stride, cudaStream_t st) {
     const int nsums = sobol_nsums(p, second), nb = sobol_nblocks(p, second);
     int nw = 4;
     while (nw > 1 && (size_t)nw * 32 * nsums * 16 > 200 * 1024) nw >>= 1;
@@ -297,9 +303,98 @@ int launch_sobol_y(const double* y, long ld_block, long count, int p, int F, int
     if ((long)ftiles > SOB_SLOTS) return set_error("F = %d too large for %d partial slots", F, SOB_SLOTS);
     BK_CUDA(cudaFuncSetAttribute(k_sobol_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ProfScope prof(PROF_SOBOL_Y, st);
-    k_sobol_y<<<nkslots * ftiles, nw * 32, smem, st>>>(y, ld_block, count, p, F, second, nb, nsums, shift, partials);
+    if (slot_stride <= 0) slot_stride = (long)F * nsums * 2;
+    k_sobol_y<<<nkslots * ftiles, nw * 32, smem, st>>>(y, ld_block, count, p, F, second, nb, nsums, shift, partials, slot_stride);
     BK_LAUNCH_CHECK("k_sobol_y");
     return 0;
+}
+
+int launch_sobol_y(const double* y, long ld_block, long count, int p, int F, int second, const double* shift,
+                   double* partials, cudaStream_t st) {
+    return launch_sobol_y_ex(y, ld_block, count, p, F, second, shift, partials, 0, st);
+}
+
+// ---------------------------------------------------------------- general kernel trees: unfused composition
+// Outputs with kind == BK_GENERAL have no fused Saltelli kernel: block b of the design is materialised for a bounded
+// slab of base rows (A / B read or drawn with Philox, one column swapped), predicted with k_predict_gen (mean only)
+// and, unless the caller wants the outputs themselves, reduced with the reducer over stored outputs (k_sobol_y).
+// Same sums, same slots; scratch comes from the stream-ordered allocator and is private to the call.
+struct BlockParams {
+    const double* a;
+    const double* b;
+    uint64_t seed;
+    long row_lo, count;
+    int p, block;          // block: 0 = A, 1 = B, 2+i = E^i, 2+p+i = C^i
+    int kind[MAX_P];
+    double pa[MAX_P], pb[MAX_P];
+    double* out;           // count x p
+};
+__global__ void k_design_block(const BlockParams prm) {
+    const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= prm.count) return;
+    const int b = prm.block, p = prm.p;
+    const bool fromB = (b == 1) || (b >= 2 + p);
+    const int swp = b < 2 ? -1 : (b < 2 + p ? b - 2 : b - 2 - p);
+    double xa[MAX_P], xb[MAX_P];
+    if (prm.a) {
+        for (int c = 0; c < p; ++c) { xa[c] = prm.a[g * p + c]; xb[c] = prm.b[g * p + c]; }
+    } else {
+        design_row<MAX_P>(prm.seed, (uint64_t)(prm.row_lo + g), p, 0, prm.kind, prm.pa, prm.pb, xa);
+        design_row<MAX_P>(prm.seed, (uint64_t)(prm.row_lo + g), p, 1, prm.kind, prm.pa, prm.pb, xb);
+    }
+    for (int c = 0; c < p; ++c) prm.out[g * p + c] = ((c == swp) != fromB) ? xb[c] : xa[c];
+}
+
+int launch_predict_general(const bk_gp_s* h, int q, const double* pts, long k, double* mean, int ld, int col,
+                           double* kstar, int8_t* kq, int kq_scheme, double kappa, cudaStream_t st);   // gp_predict_gen.cu
+
+static int launch_sobol_general(const bk_gp_s* h, int q, const double* a, const double* b, uint64_t seed,
+                                const int* mkind, const double* mpar, long row_lo, long count, int second,
+                                double shift, double* partials, double* yout, cudaStream_t st) {
+    const int p = h->p, nb = sobol_nblocks(p, second), nsums = sobol_nsums(p, second);
+    const long SLAB = 1L << 18;                       // base rows per slab: scratch <= 2^18 * (p + nb + 1) doubles
+    const long slab_max = count < SLAB ? count : SLAB;
+    double* design = nullptr;
+    double* ybuf = nullptr;
+    double* shift_dev = nullptr;
+    BK_CUDA(cudaMallocAsync(&design, sizeof(double) * slab_max * p, st));
+    if (!yout) {
+        BK_CUDA(cudaMallocAsync(&ybuf, sizeof(double) * slab_max * nb, st));
+        BK_CUDA(cudaMallocAsync(&shift_dev, sizeof(double), st));
+        BK_CUDA(cudaMemcpyAsync(shift_dev, &shift, sizeof(double), cudaMemcpyHostToDevice, st));
+        BK_CUDA(cudaStreamSynchronize(st));            // `shift` is a stack value
+    }
+    BlockParams bp;
+    bp.seed = seed; bp.p = p;
+    for (int c = 0; c < MAX_P; ++c) {
+        bp.kind[c] = (c < p && mkind) ? mkind[c] : 0;
+        bp.pa[c] = (c < p && mpar) ? mpar[2 * c] : 0.0;
+        bp.pb[c] = (c < p && mpar) ? mpar[2 * c + 1] : 0.0;
+    }
+    int rc = 0;
+    for (long lo = 0; lo < count && rc == 0; lo += SLAB) {
+        const long cnt = (count - lo) < SLAB ? (count - lo) : SLAB;
+        bp.a = a ? a + lo * p : nullptr;
+        bp.b = b ? b + lo * p : nullptr;
+        bp.row_lo = row_lo + lo; bp.count = cnt; bp.out = design;
+        for (int blk = 0; blk < nb && rc == 0; ++blk) {
+            bp.block = blk;
+            k_design_block<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(bp);
+            if (cudaGetLastError() != cudaSuccess) { rc = set_error("k_design_block launch failed"); break; }
+            if (yout)     // yout[(blk * count + lo + k) * m + q]
+                rc = launch_predict_general(h, q, design, cnt, yout + ((size_t)blk * count + lo) * h->m, h->m, q, nullptr,
+                                            nullptr, 0, 1.0, st);
+            else          // ybuf[blk * cnt + k]
+                rc = launch_predict_general(h, q, design, cnt, ybuf + (size_t)blk * cnt, 1, 0, nullptr, nullptr, 0, 1.0, st);
+        }
+        if (rc == 0 && !yout)
+            rc = launch_sobol_y_ex(ybuf, cnt, cnt, p, 1, second, shift_dev, partials + (size_t)q * nsums * 2,
+                                   (long)h->m * nsums * 2, st);
+    }
+    cudaFreeAsync(design, st);
+    if (ybuf) cudaFreeAsync(ybuf, st);
+    if (shift_dev) cudaFreeAsync(shift_dev, st);
+    return rc;
 }
 
 // ---------------------------------------------------------------- slots -> totals -> indices

@@ -5,6 +5,7 @@ C handle; every computation goes through the C ABI.  Data layout in HBM, per
 output q (DESIGN.md §"Data layout"):
 
 * ``xs[q]``     (n_pad, P) float64   X_train / length_scale, zero padded
+                (general kernel trees: (n_pad, nf*P), one scaled copy per stationary leaf)
 * ``alpha[q]``  (n_pad,)   float64   K^-1 y (sklearn ``alpha_``), zero padded
 * ``wt[q]``     (n_pad*n_pad,) float64  L^-1 packed in DMMA-fragment tiles
                 (built lazily: only sigma needs it)
@@ -54,9 +55,19 @@ class DeviceModel:
             self.wq = [w[1] if w is not None else None for w in wts] if wts is not None else [None] * self.m
             self.wsig = [w[2] if w is not None else None for w in wts] if wts is not None else [None] * self.m
             for q, spec in enumerate(specs):
-                ls = torch.from_numpy(np.asarray(spec.ls, dtype=np.float64)).to(self.device)
-                xs = torch.zeros((self.n_pad, self.P), dtype=torch.float64, device=self.device)
-                xs[:self.n, :self.p] = Xd / ls            # IEEE division, same bits as numpy's X / length_scale
+                if spec.general is not None:
+                    g = spec.general
+                    if g.nf * self.P > 48:
+                        raise NotImplementedError(
+                            "kernel tree with %d stationary leaves at input dimension %d exceeds the staging "
+                            "buffers of the general device kernel (leaves x padded dimension <= 48)" % (g.nf, self.p))
+                    xs = torch.zeros((self.n_pad, g.nf * self.P), dtype=torch.float64, device=self.device)
+                    for f in range(g.nf):
+                        xs[:self.n, f * self.P:f * self.P + self.p] = Xd / torch.from_numpy(g.fls[f]).to(self.device)
+                else:
+                    ls = torch.from_numpy(np.asarray(spec.ls, dtype=np.float64)).to(self.device)
+                    xs = torch.zeros((self.n_pad, self.P), dtype=torch.float64, device=self.device)
+                    xs[:self.n, :self.p] = Xd / ls        # IEEE division, same bits as numpy's X / length_scale
                 al = torch.zeros(self.n_pad, dtype=torch.float64, device=self.device)
                 al[:self.n] = torch.from_numpy(np.ascontiguousarray(alphas[q], dtype=np.float64).ravel()).to(self.device)
                 self.xs.append(xs)
@@ -96,9 +107,16 @@ class DeviceModel:
     # -- C handle ------------------------------------------------------------------------------
     def _set_output(self, q):
         spec = self.specs[q]
-        _lib.check(self.lib.bk_gp_set_output(
-            self.handle, q, spec.kind, spec.c0, spec.c1, spec.kdiag, _lib.as_double_array(spec.ls),
-            _ptr(self.xs[q]), _ptr(self.alpha[q]), _ptr(self.wt[q]), self.y_means[q], self.y_stds[q]))
+        if spec.general is not None:
+            g = spec.general
+            _lib.check(self.lib.bk_gp_set_output_general(
+                self.handle, q, g.nf, _lib.as_int_array(g.fkind), _lib.as_double_array(g.fls.ravel()), g.nt,
+                _lib.as_double_array(g.tcoef), _lib.as_int_array(g.texp.ravel()), spec.kdiag,
+                _ptr(self.xs[q]), _ptr(self.alpha[q]), _ptr(self.wt[q]), self.y_means[q], self.y_stds[q]))
+        else:
+            _lib.check(self.lib.bk_gp_set_output(
+                self.handle, q, spec.kind, spec.c0, spec.c1, spec.kdiag, _lib.as_double_array(spec.ls),
+                _ptr(self.xs[q]), _ptr(self.alpha[q]), _ptr(self.wt[q]), self.y_means[q], self.y_stds[q]))
         _lib.check(self.lib.bk_gp_set_output_int8(self.handle, q, _ptr(self.wq[q]), _ptr(self.wsig[q])))
 
     def set_scaler(self, scale, mn):

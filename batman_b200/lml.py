@@ -50,6 +50,21 @@ def lml_batched(X_dev, y_dev, specs):
             r = len(sl)
             ws = _workspace(X_dev.device, lib.bk_lml_workspace(n, r, 0))
             lml = torch.empty(r, dtype=torch.float64, device=X_dev.device)
+            if sl[0].general is not None:
+                # candidates of one fit share the tree shape (clone_with_theta only moves the values)
+                g0 = sl[0].general
+                if any(s.general is None or s.general.shape_key() != g0.shape_key() for s in sl):
+                    raise ValueError("lml_batched: candidates of one batch must share the kernel tree")
+                _lib.check(lib.bk_lml_batched_general(
+                    _ptr(X_dev), _ptr(y_dev), n, p, r, g0.nf, _lib.as_int_array(g0.fkind), g0.nt,
+                    _lib.as_int_array(g0.texp.ravel()),
+                    _lib.as_double_array(np.concatenate([s.general.tcoef for s in sl])),
+                    _lib.as_double_array(np.concatenate([s.general.fls.ravel() for s in sl])),
+                    _lib.as_double_array([s.kdiag for s in sl]), _ptr(lml), _ptr(ws), ws.numel(), _stream()))
+                out[lo:lo + r] = lml.cpu().numpy()
+                continue
+            if any(s.general is not None for s in sl):
+                raise ValueError("lml_batched: candidates of one batch must share the kernel tree")
             kinds = _lib.as_int_array([s.kind for s in sl])
             c0 = _lib.as_double_array([s.c0 for s in sl])
             c1 = _lib.as_double_array([s.c1 for s in sl])
@@ -65,7 +80,7 @@ def int8_scheme(n, specs):
     """Slicing scheme of the int8 sigma kernel for a model: 1 (7 x 8-bit, fewer MMAs) when the int32 accumulation
     stays exact (n_pad <= 8192) and every covariance is non-negative (K* is sliced into unsigned bytes), else 0."""
     n_pad = _lib.load().bk_gp_padded_n(n)
-    return 1 if n_pad <= 8192 and all(s.c0 >= 0.0 and s.c1 >= 0.0 for s in specs) else 0
+    return 1 if n_pad <= 8192 and all(s.nonneg for s in specs) else 0
 
 
 def factorise(X_dev, y_dev, spec):
@@ -87,10 +102,18 @@ def factorise(X_dev, y_dev, spec):
         wsig = torch.empty(n_pad, dtype=torch.float64, device=dev)
         lml = torch.empty(1, dtype=torch.float64, device=dev)
         info = torch.zeros(1, dtype=torch.int32, device=dev)
-        _lib.check(lib.bk_gp_factorise(_ptr(X_dev), _ptr(y_dev), n, p, spec.kind, spec.c0, spec.c1, spec.kdiag,
-                                       _lib.as_double_array(spec.ls), _ptr(L), _ptr(alpha), _ptr(wt), _ptr(wq),
-                                       _ptr(wsig), int8_scheme(n, [spec]), _ptr(lml), _ptr(info), _ptr(ws), ws.numel(),
-                                       _stream()))
+        if spec.general is not None:
+            g = spec.general
+            _lib.check(lib.bk_gp_factorise_general(
+                _ptr(X_dev), _ptr(y_dev), n, p, g.nf, _lib.as_int_array(g.fkind), g.nt,
+                _lib.as_int_array(g.texp.ravel()), _lib.as_double_array(g.tcoef), _lib.as_double_array(g.fls.ravel()),
+                spec.kdiag, _ptr(L), _ptr(alpha), _ptr(wt), _ptr(wq), _ptr(wsig), int8_scheme(n, [spec]), _ptr(lml),
+                _ptr(info), _ptr(ws), ws.numel(), _stream()))
+        else:
+            _lib.check(lib.bk_gp_factorise(_ptr(X_dev), _ptr(y_dev), n, p, spec.kind, spec.c0, spec.c1, spec.kdiag,
+                                           _lib.as_double_array(spec.ls), _ptr(L), _ptr(alpha), _ptr(wt), _ptr(wq),
+                                           _ptr(wsig), int8_scheme(n, [spec]), _ptr(lml), _ptr(info), _ptr(ws),
+                                           ws.numel(), _stream()))
         if int(info.item()) != 0:
             raise np.linalg.LinAlgError(
                 "The kernel is not returning a positive definite matrix. Try gradually increasing the "

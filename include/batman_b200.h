@@ -34,7 +34,8 @@ enum bk_kind {
     BK_MATERN32 = 1,  /* (1 + sqrt3 r) exp(-sqrt3 r)               Matern(nu=1.5), batman default kriging.py:85-88 */
     BK_MATERN52 = 2,  /* (1 + sqrt5 r + 5r^2/3) exp(-sqrt5 r)      Matern(nu=2.5) */
     BK_RBF = 3,       /* exp(-0.5 r^2) on the squared distance     RBF */
-    BK_MATERN_INF = 4 /* exp(-(r*r)/2) on the rooted distance      Matern(nu=inf) */
+    BK_MATERN_INF = 4, /* exp(-(r*r)/2) on the rooted distance     Matern(nu=inf) */
+    BK_GENERAL = 5     /* expanded Sum/Product tree with several stationary leaves (bk_gp_set_output_general) */
 };
 
 enum bk_marginal_kind { BK_UNIFORM = 0, BK_NORMAL = 1 };
@@ -69,6 +70,15 @@ size_t bk_gp_wtiles_len(int n_train);
 int bk_gp_set_output(bk_gp_t h, int q, int kind, double c0, double c1, double kdiag,
                      const double* ls_host, const double* xs_dev, const double* alpha_dev,
                      const double* w_tiles_dev, double y_mean, double y_std);
+/* General Sum/Product trees over ConstantKernel / WhiteKernel / RBF / Matern leaves (sklearn:kernels.py:838-871,
+ * 936-990; the reference accepts any such expression, kriging.py:80-96, driver.py:181-190), expanded by the host to
+ *     k(x, x') = sum_{t < nt} tcoef[t] * prod_{f < nf} stat_{fkind[f]}(||(x - x')/ls_f||) ^ texp[t*nf + f]
+ * with nf <= 3 stationary leaves, nt <= 6 terms and nf * bk_gp_padded_dim(p) <= 48.  fls_host is nf x p,
+ * xs_dev is row-major n_pad x (nf * P): row j = [X_j/ls_0 | X_j/ls_1 | ...], each part zero padded to P.
+ * Trees with ONE leaf and an affine expansion go through bk_gp_set_output (the fast kernels). */
+int bk_gp_set_output_general(bk_gp_t h, int q, int nf, const int* fkind_host, const double* fls_host, int nt,
+                             const double* tcoef_host, const int* texp_host, double kdiag, const double* xs_dev,
+                             const double* alpha_dev, const double* w_tiles_dev, double y_mean, double y_std);
 /* Optional int8 image of L^-1 for the tcgen05 variance kernel (error-free 8 x 7-bit slicing, csrc/var_ozaki.cu):
  * wq_dev bk_gp_wq_bytes(n) bytes of slice tiles, wsig_dev n_pad power-of-two row scales; both produced by
  * bk_tri_inverse_pack / bk_gp_factorise with wq_scheme 0 (8 signed 7-bit slices, n_train <= 16384) or 1 (7 8-bit
@@ -105,12 +115,24 @@ int bk_lml_batched(const double* x_dev, const double* y_dev, int n_train, int p,
                    const int* kind_host, const double* c0_host, const double* c1_host, const double* kdiag_host,
                    const double* ls_host /* R x p */, double* lml_dev, void* workspace_dev, size_t workspace_bytes,
                    void* stream);
+/* The same for general trees (bk_gp_set_output_general): the tree shape (nf, fkind, nt, texp) is shared by the
+ * candidates; tcoef_host is R x nt, fls_host R x nf x p, kdiag_host R. */
+int bk_lml_batched_general(const double* x_dev, const double* y_dev, int n_train, int p, int n_candidates, int nf,
+                           const int* fkind_host, int nt, const int* texp_host, const double* tcoef_host,
+                           const double* fls_host, const double* kdiag_host, double* lml_dev, void* workspace_dev,
+                           size_t workspace_bytes, void* stream);
 /* Final state at one theta: l_dev (n_pad x n_pad row-major, lower triangle = L_), alpha_dev (n_pad) = alpha_,
  * w_tiles_dev (bk_gp_wtiles_len doubles or NULL) = packed L^-1, lml_dev (1), info_dev (1; 0 = positive definite). */
 int bk_gp_factorise(const double* x_dev, const double* y_dev, int n_train, int p, int kind, double c0, double c1,
                     double kdiag, const double* ls_host, double* l_dev, double* alpha_dev, double* w_tiles_dev,
                     int8_t* wq_dev /* or NULL */, double* wsig_dev /* or NULL */, int wq_scheme, double* lml_dev,
                     int* info_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+int bk_gp_factorise_general(const double* x_dev, const double* y_dev, int n_train, int p, int nf,
+                            const int* fkind_host, int nt, const int* texp_host, const double* tcoef_host,
+                            const double* fls_host, double kdiag, double* l_dev, double* alpha_dev,
+                            double* w_tiles_dev, int8_t* wq_dev /* or NULL */, double* wsig_dev /* or NULL */,
+                            int wq_scheme, double* lml_dev, int* info_dev, void* workspace_dev,
+                            size_t workspace_bytes, void* stream);
 /* Packed L^-1 tiles from a given Cholesky factor l_dev (n x n row-major lower), e.g. scikit-learn's L_;
  * workspace: bk_lml_workspace(n, 1, 1). */
 int bk_tri_inverse_pack(const double* l_dev, int n_train, double* w_tiles_dev, int8_t* wq_dev /* or NULL */,

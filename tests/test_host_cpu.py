@@ -61,10 +61,39 @@ def test_kernel_flatten_matches_sklearn_semantics():
         np.testing.assert_allclose(np.full(7, spec.kdiag), k.diag(X), rtol=1e-15)
 
 
+def test_kernel_flatten_general_trees():
+    """Trees with several stationary leaves expand to sum_t coef_t prod_f stat_f^e_tf (SURVEY §8 A5 note)."""
+    rng = np.random.RandomState(1)
+    X, Y = rng.rand(7, 3), rng.rand(5, 3)
+    cases = [
+        sk.ConstantKernel(2.0) * sk.RBF(length_scale=[1.0, 2.0, 0.5]) * sk.Matern(length_scale=0.7, nu=2.5),
+        sk.ConstantKernel(1.5) * sk.RBF(length_scale=1.0) + sk.ConstantKernel(0.5) * sk.Matern(length_scale=2.0, nu=0.5)
+        + sk.WhiteKernel(0.01),
+        (sk.ConstantKernel(2.0) + sk.RBF(length_scale=1.0)) * (sk.ConstantKernel(3.0) + sk.Matern(length_scale=0.4)),
+        sk.RBF(length_scale=1.3) * sk.RBF(length_scale=1.3),
+        sk.Matern(length_scale=1.0, nu=0.5) + sk.Matern(length_scale=2.0, nu=1.5) + sk.Matern(length_scale=3.0, nu=np.inf),
+    ]
+    stat = {kernel_spec.KIND_MATERN12: lambda r: np.exp(-r),
+            kernel_spec.KIND_MATERN32: lambda r: (1 + np.sqrt(3) * r) * np.exp(-np.sqrt(3) * r),
+            kernel_spec.KIND_MATERN52: lambda r: (1 + np.sqrt(5) * r + 5 * r * r / 3) * np.exp(-np.sqrt(5) * r),
+            kernel_spec.KIND_RBF: lambda r: np.exp(-0.5 * r * r),
+            kernel_spec.KIND_MATERN_INF: lambda r: np.exp(-0.5 * r * r)}
+    for k in cases:
+        spec = kernel_spec.flatten(k, 3)
+        g = spec.general
+        assert spec.kind == kernel_spec.KIND_GENERAL and g is not None
+        fv = [stat[g.fkind[f]](np.sqrt((((X[:, None, :] - Y[None, :, :]) / g.fls[f]) ** 2).sum(-1))) for f in range(g.nf)]
+        val = sum(g.tcoef[t] * np.prod([fv[f] ** g.texp[t, f] for f in range(g.nf)], axis=0) for t in range(g.nt))
+        np.testing.assert_allclose(val, k(X, Y), rtol=1e-13, atol=1e-15)
+        np.testing.assert_allclose(np.full(7, spec.kdiag), k.diag(X), rtol=1e-15)
+        assert spec.nonneg
+
+
 def test_kernel_flatten_rejects_unsupported():
-    for k in [sk.RationalQuadratic(), sk.Matern(nu=1.0), sk.DotProduct(),
-              sk.Matern(length_scale=1.0) * sk.RBF(length_scale=2.0),
-              sk.Matern(length_scale=1.0) + sk.RBF(length_scale=2.0)]:
+    four = sk.Matern(length_scale=1.0) + sk.RBF(length_scale=2.0) + sk.Matern(length_scale=3.0, nu=0.5) \
+        + sk.Matern(length_scale=4.0, nu=2.5)                           # 4 distinct stationary leaves
+    for k in [sk.RationalQuadratic(), sk.Matern(nu=1.0), sk.DotProduct(), four,
+              sk.ConstantKernel(2.0) * sk.ExpSineSquared()]:
         with pytest.raises(NotImplementedError):
             kernel_spec.flatten(k, 2)
     with pytest.raises(ValueError):

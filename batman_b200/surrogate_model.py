@@ -118,6 +118,32 @@ class SurrogateModel:
         self.space.doe_init = len(sample)
         self.update = False
 
+    def estimate_quality(self, method='LOO'):
+        """Leave-one-out Q2 and the point of largest error (surrogate_model.py:200-269).
+
+        As in the reference every fold REFITS the predictor (hyper-parameters included) on n - 1 points and predicts
+        the held-out one; the folds run one after the other on the device instead of in a fork pool."""
+        from sklearn.metrics import r2_score
+        if self.pod is not None:
+            raise NotImplementedError("estimate_quality with a POD is Pod.estimate_quality (pod.py:264-420): "
+                                      "use the reference for that path")
+        self.logger.info('Estimating Surrogate quality...')
+        sample = np.array(self.space, dtype=np.float64)
+        data = np.asarray(self.data, dtype=np.float64).reshape(len(sample), -1)
+        sample_scaled = self.scaler.transform(sample)
+        y_pred = np.empty_like(data)
+        keep = np.ones(len(sample), dtype=bool)
+        for i in range(len(sample)):
+            keep[i] = False
+            fold = Kriging(sample_scaled[keep], data[keep], **self.settings)
+            y_pred[i] = fold.evaluate(sample_scaled[i])[0][0]
+            keep[i] = True
+        q2_loo = r2_score(data, y_pred)
+        index = ((data - y_pred) ** 2).sum(axis=1).argmax()
+        point = self.space[index]
+        self.logger.info('Surrogate quality: {}, max error location at {}'.format(q2_loo, point))
+        return q2_loo, point
+
     # ------------------------------------------------------------------ device-level call used by UQ
     def predict_device(self, raw_points_dev, return_std=True):
         """raw (unscaled) points on the device -> (results, sigma) on the device, POD applied."""

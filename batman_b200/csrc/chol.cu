@@ -27,6 +27,7 @@
 namespace bk {
 
 constexpr int NB = 128;
+constexpr int SPLIT_MAX = 8;       // split-K slices of the diagonal block-row update
 constexpr double JITTER = 1e-10;   // GaussianProcessRegressor(alpha=1e-10), sklearn:_gpr.py:215
 
 // ---------------------------------------------------------------- candidate parameters (device copy)
@@ -95,6 +96,7 @@ struct GemmArgs {
     double* C; long c_batch, c_tile; int ldc;
     int K0, k_tile;          // K = K0 + blockIdx.x * k_tile   (multiple of 16)
     double alpha, beta;
+    int split_k_total = 0;   // > 0: split-K, tile x covers columns [x*K0, min((x+1)*K0, split_k_total)) (a_tile = b_tile = K0)
 };
 constexpr int G_BK = 16, G_PITCH = 20, G_STAGES = 3;     // pitch 20 doubles: conflict-free fragment loads
 constexpr size_t G_SMEM = (size_t)G_STAGES * 2 * NB * G_PITCH * 8;
@@ -113,7 +115,8 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt(const GemmArgs g) {
     const double* A = g.A + (size_t)blockIdx.y * g.a_batch + (size_t)blockIdx.x * g.a_tile;
     const double* B = g.B + (size_t)blockIdx.y * g.b_batch + (size_t)blockIdx.x * g.b_tile;
     double* C = g.C + (size_t)blockIdx.y * g.c_batch + (size_t)blockIdx.x * g.c_tile;
-    const int K = g.K0 + (int)blockIdx.x * g.k_tile;
+    int K = g.K0 + (int)blockIdx.x * g.k_tile;
+    if (g.split_k_total > 0 && (int)(blockIdx.x + 1) * g.K0 > g.split_k_total) K = g.split_k_total - (int)blockIdx.x * g.K0;
     const int nk = K / G_BK;
 
     auto load_stage = [&](int s, int kb) {
@@ -187,6 +190,22 @@ static int gemm_nt(const GemmArgs& g, int tiles, int batch, cudaStream_t st) {
     return 0;
 }
 
+// ---------------------------------------------------------------- s = y_k - L[k, <k] z_<k, one warp per row
+// (16 CTAs per candidate instead of a serial prologue inside the single-CTA diagonal-block kernel)
+__global__ void __launch_bounds__(256) k_zdot(const double* __restrict__ M, long m_batch, int ld, int k,
+                                              const double* __restrict__ y, const double* __restrict__ z,
+                                              long z_batch, double* __restrict__ sv) {
+    const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.y * 8 + warp;
+    const double* row = M + (size_t)r * m_batch + (size_t)(k * NB + i) * ld;
+    const double* zr = z + (size_t)r * z_batch;
+    double part = 0.0;
+    for (int j = lane; j < k * NB; j += 32) part = fma(row[j], zr[j], part);     // lanes stride the columns (coalesced)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) sv[(size_t)r * NB + i] = y[k * NB + i] - part;
+}
+
 // ---------------------------------------------------------------- diagonal block: factor, invert, forward-solve
 constexpr int DP = NB + 1;   // shared pitch
 constexpr size_t DIAG_SMEM = ((size_t)NB * DP + 2 * NB) * 8;
@@ -214,8 +233,9 @@ __device__ void tri_invert_smem(double* a) {
 template <bool FACTOR>
 __global__ void __launch_bounds__(256, 1)
 k_diag_block(double* __restrict__ M, long m_batch, int ld, int k, double* __restrict__ Winv, long w_batch,
-             double* __restrict__ WT, long wt_batch, const double* __restrict__ y, double* __restrict__ z,
-             long z_batch, double* __restrict__ acc /* [R][2]: logdet, zz */, int* __restrict__ info) {
+             double* __restrict__ WT, long wt_batch, const double* __restrict__ sv_in /* [R][NB] from k_zdot */,
+             double* __restrict__ z, long z_batch, double* __restrict__ acc /* [R][2]: logdet, zz */,
+             int* __restrict__ info, const double* __restrict__ part /* [R][SPLIT_MAX][NB*NB] */, int nsplit) {
     extern __shared__ __align__(16) double sm[];
     double* a = sm;                  // [NB][DP]
     double* sv = sm + NB * DP;       // [NB] rhs of the forward solve
@@ -226,19 +246,13 @@ k_diag_block(double* __restrict__ M, long m_batch, int ld, int k, double* __rest
     double* blk = Mr + (size_t)k * NB * ld + (size_t)k * NB;
     for (int idx = tid; idx < NB * NB; idx += 256) {
         const int i = idx >> 7, cidx = idx & 127;
-        a[i * DP + cidx] = cidx <= i ? blk[(size_t)i * ld + cidx] : 0.0;
+        double v = cidx <= i ? blk[(size_t)i * ld + cidx] : 0.0;
+        if (cidx <= i)      // T_kk = A_kk - sum_s (L[k, slice s] L[k, slice s]^T), fixed order
+            for (int sp = 0; sp < nsplit; ++sp) v -= part[((size_t)r * SPLIT_MAX + sp) * NB * NB + idx];
+        a[i * DP + cidx] = v;
     }
     if constexpr (FACTOR) {
-        // s = y_k - L[k, <k] z_<k : 8 warps x 16 rows, lanes stride the columns (coalesced)
-        const double* zr = z + (size_t)r * z_batch;
-        for (int i = warp * 16; i < warp * 16 + 16; ++i) {
-            const double* row = Mr + (size_t)(k * NB + i) * ld;
-            double part = 0.0;
-            for (int j = lane; j < k * NB; j += 32) part = fma(row[j], zr[j], part);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            if (lane == 0) sv[i] = y[k * NB + i] - part;
-        }
+        if (tid < NB) sv[tid] = sv_in[(size_t)r * NB + tid];       // s = y_k - L[k, <k] z_<k (k_zdot)
         // unblocked right-looking Cholesky in shared memory
         int bad = 0;
         for (int j = 0; j < NB; ++j) {
@@ -335,7 +349,7 @@ __global__ void k_pad_copy_lower(const double* __restrict__ L, int n, int n_pad,
 
 // ---------------------------------------------------------------- host orchestration
 struct LmlWorkspace {
-    Cand* cands; double* M; double* Winv; double* z; double* acc; int* info; double* ypad;
+    Cand* cands; double* M; double* Winv; double* z; double* acc; int* info; double* ypad; double* sv; double* part;
 };
 static size_t align_up(size_t v) { return (v + 255) / 256 * 256; }
 
@@ -349,6 +363,8 @@ size_t lml_workspace_bytes(int n, int R, bool with_wt) {
     b += align_up(sizeof(double) * 2 * R);                    // acc
     b += align_up(sizeof(int) * R);                           // info
     b += align_up(sizeof(double) * n_pad);                    // y padded
+    b += align_up(sizeof(double) * NB * R);                   // right-hand side of the block forward solve
+    b += align_up(sizeof(double) * SPLIT_MAX * NB * NB * R);  // split-K partials of the diagonal block-row update
     if (with_wt) b += align_up(sizeof(double) * n_pad * n_pad * R);
     return b;
 }
@@ -363,6 +379,8 @@ static LmlWorkspace carve(void* ws, int n, int R, double** wt_out) {
     w.acc = (double*)p; p += align_up(sizeof(double) * 2 * R);
     w.info = (int*)p; p += align_up(sizeof(int) * R);
     w.ypad = (double*)p; p += align_up(sizeof(double) * n_pad);
+    w.sv = (double*)p; p += align_up(sizeof(double) * NB * R);
+    w.part = (double*)p; p += align_up(sizeof(double) * SPLIT_MAX * NB * NB * R);
     if (wt_out) *wt_out = (double*)p;
     return w;
 }
@@ -403,6 +421,29 @@ static int general_cands(std::vector<Cand>& h, int R, int p, int nf, const int* 
     return 0;
 }
 
+// Side stream (highest priority) for the latency-bound single-CTA diagonal-block kernel: it runs while the main
+// stream updates the block rows below the diagonal (look-ahead), so only the row-k update sits on the critical path.
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t e_main = nullptr, e_side = nullptr;
+};
+static int side_stream(SideStream** out) {
+    static SideStream per_dev[64];
+    int dev = 0;
+    BK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return set_error("device ordinal %d out of range", dev);
+    SideStream& ss = per_dev[dev];
+    if (!ss.s) {
+        int lo = 0, hi = 0;
+        BK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        BK_CUDA(cudaStreamCreateWithPriority(&ss.s, cudaStreamNonBlocking, hi));
+        BK_CUDA(cudaEventCreateWithFlags(&ss.e_main, cudaEventDisableTiming));
+        BK_CUDA(cudaEventCreateWithFlags(&ss.e_side, cudaEventDisableTiming));
+    }
+    *out = &ss;
+    return 0;
+}
+
 // blocked Cholesky of the R matrices in w.M (in place), z and the accumulators alongside
 static int cholesky_sweep(const LmlWorkspace& w, int n, int R, double* WT, cudaStream_t st) {
     const int n_pad = padded_n(n), nP = n_pad / NB;
@@ -413,22 +454,47 @@ static int cholesky_sweep(const LmlWorkspace& w, int n, int R, double* WT, cudaS
         BK_CUDA(cudaFuncSetAttribute(k_diag_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
         attr = true;
     }
+    SideStream* ss = nullptr;
+    if (int rc = side_stream(&ss)) return rc;
     BK_CUDA(cudaMemsetAsync(w.acc, 0, sizeof(double) * 2 * R, st));
     BK_CUDA(cudaMemsetAsync(w.info, 0, sizeof(int) * R, st));
+    // T_ik = A_ik - L[i, <k] L[k, <k]^T for the block rows i = i0 .. i0 + tiles - 1
+    auto update = [&](int k, int i0, int tiles) {
+        GemmArgs g;
+        g.A = w.M + (size_t)i0 * NB * n_pad; g.a_batch = mb; g.a_tile = (long)NB * n_pad; g.lda = n_pad;
+        g.B = w.M + (size_t)k * NB * n_pad; g.b_batch = mb; g.b_tile = 0; g.ldb = n_pad;
+        g.C = w.M + (size_t)i0 * NB * n_pad + (size_t)k * NB; g.c_batch = mb; g.c_tile = (long)NB * n_pad; g.ldc = n_pad;
+        g.K0 = k * NB; g.k_tile = 0; g.alpha = -1.0; g.beta = 1.0;
+        return gemm_nt(g, tiles, R, st);
+    };
     for (int k = 0; k < nP; ++k) {
-        if (k > 0) {   // T_ik = A_ik - L[i, <k] L[k, <k]^T, i = k..nP-1
+        int nsplit = 0;
+        if (k > 0) {
+            // the diagonal block first, split-K over up to SPLIT_MAX CTAs per candidate: partial products go to
+            // scratch and are subtracted by the diagonal-block kernel when it loads T_kk
+            const int per = (k + SPLIT_MAX - 1) / SPLIT_MAX;               // 128-column blocks per slice
+            nsplit = (k + per - 1) / per;
             GemmArgs g;
-            g.A = w.M + (size_t)k * NB * n_pad; g.a_batch = mb; g.a_tile = (long)NB * n_pad; g.lda = n_pad;
-            g.B = w.M + (size_t)k * NB * n_pad; g.b_batch = mb; g.b_tile = 0; g.ldb = n_pad;
-            g.C = w.M + (size_t)k * NB * n_pad + (size_t)k * NB; g.c_batch = mb; g.c_tile = (long)NB * n_pad; g.ldc = n_pad;
-            g.K0 = k * NB; g.k_tile = 0; g.alpha = -1.0; g.beta = 1.0;
-            if (int rc = gemm_nt(g, nP - k, R, st)) return rc;
+            g.A = w.M + (size_t)k * NB * n_pad; g.a_batch = mb; g.a_tile = (long)per * NB; g.lda = n_pad;
+            g.B = g.A; g.b_batch = mb; g.b_tile = (long)per * NB; g.ldb = n_pad;
+            g.C = w.part; g.c_batch = (long)SPLIT_MAX * NB * NB; g.c_tile = (long)NB * NB; g.ldc = NB;
+            g.K0 = per * NB; g.k_tile = 0; g.alpha = 1.0; g.beta = 0.0; g.split_k_total = k * NB;
+            if (int rc = gemm_nt(g, nsplit, R, st)) return rc;
         }
+        BK_CUDA(cudaEventRecord(ss->e_main, st));
+        BK_CUDA(cudaStreamWaitEvent(ss->s, ss->e_main, 0));
         {
-            ProfScope prof(PROF_CHOL, st);
-            k_diag_block<true><<<R, 256, DIAG_SMEM, st>>>(w.M, mb, n_pad, k, w.Winv, wb, WT, mb, w.ypad, w.z, n_pad, w.acc, w.info);
+            ProfScope prof(PROF_CHOL, ss->s);
+            k_zdot<<<dim3(R, NB / 8), 256, 0, ss->s>>>(w.M, mb, n_pad, k, w.ypad, w.z, n_pad, w.sv);
+            BK_LAUNCH_CHECK("k_zdot");
+            k_diag_block<true><<<R, 256, DIAG_SMEM, ss->s>>>(w.M, mb, n_pad, k, w.Winv, wb, WT, mb, w.sv, w.z, n_pad, w.acc, w.info,
+                                                             w.part, nsplit);
             BK_LAUNCH_CHECK("k_diag_block<true>");
         }
+        BK_CUDA(cudaEventRecord(ss->e_side, ss->s));
+        if (k > 0 && k + 1 < nP)
+            if (int rc = update(k, k + 1, nP - k - 1)) return rc;          // rows below: overlaps the diagonal block
+        BK_CUDA(cudaStreamWaitEvent(st, ss->e_side, 0));
         if (k + 1 < nP) {   // L_ik = T_ik Winv_k^T, i = k+1..nP-1 (in place)
             GemmArgs g;
             g.A = w.M + (size_t)(k + 1) * NB * n_pad + (size_t)k * NB; g.a_batch = mb; g.a_tile = (long)NB * n_pad; g.lda = n_pad;
@@ -583,7 +649,8 @@ int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, int8_t* wq_ou
     BK_CUDA(cudaMemsetAsync(WT, 0, sizeof(double) * n_pad * n_pad, st));
     for (int k = 0; k < nP; ++k) {
         ProfScope prof(PROF_CHOL, st);
-        k_diag_block<false><<<1, 256, DIAG_SMEM, st>>>(w.M, 0, n_pad, k, w.Winv, 0, WT, 0, nullptr, nullptr, 0, nullptr, nullptr);
+        k_diag_block<false><<<1, 256, DIAG_SMEM, st>>>(w.M, 0, n_pad, k, w.Winv, 0, WT, 0, nullptr, nullptr, 0, nullptr, nullptr,
+                                                       nullptr, 0);
         BK_LAUNCH_CHECK("k_diag_block<false>");
     }
     if (int rc = trtri_sweep(w.M, w.Winv, WT, n, st)) return rc;

@@ -9,6 +9,7 @@ loaded with ctypes).  There is no CPU fallback.
 """
 from ._lib import BatmanB200Error, load as load_library  # noqa: F401
 from .kriging import Kriging  # noqa: F401
+from .mixture import Mixture  # noqa: F401
 from .multifidelity import Evofusion  # noqa: F401
 from .refine import Refiner  # noqa: F401
 from .surrogate_model import Pod, SurrogateModel  # noqa: F401

@@ -111,3 +111,54 @@ def test_refiner_sigma_and_expected_improvement():
     d1 = min_value - m1[0, 0]
     ei1 = d1 * norm.cdf(d1 / np.sqrt(s1[0, 0])) + np.sqrt(s1[0, 0]) * norm.pdf(d1 / np.sqrt(s1[0, 0]))
     assert ei1 >= 0.9 * ei[far].max()
+
+
+def test_mixture_fixed_theta_equals_manual_pipeline():
+    """surrogate/mixture.py:100-205, 305-353: cluster -> classify -> local Kriging, against the same pipeline
+    assembled by hand from scikit-learn objects at a fixed kernel."""
+    from sklearn.cluster import KMeans
+    from sklearn.svm import SVC
+    from batman_b200 import Mixture
+    rng = np.random.RandomState(5)
+    corners = np.array([[0.0, 0.0], [2.0, 1.0]])
+    X = corners[0] + ofun.halton(60, 2) * (corners[1] - corners[0])
+    step = (X[:, :1] > 1.0).astype(float)
+    data = np.hstack([np.sin(3 * X[:, :1]) + 10 * step + X[:, 1:], np.cos(2 * X[:, 1:]) - 10 * step])
+    kern = sk.ConstantKernel(1.0, 'fixed') * sk.Matern([0.4, 0.6], 'fixed', nu=2.5)
+    local = [{'kriging': {'kernel': kern}}] * 2
+    mix = Mixture(X, data, corners, local_method=local, clusterer=KMeans(n_clusters=2, n_init=10, random_state=0),
+                  classifier=SVC())
+    assert sorted(len(v) for v in mix.indice_clt.values()) == sorted([int(step.sum()), int(60 - step.sum())])
+    pts = corners[0] + rng.rand(300, 2) * (corners[1] - corners[0])
+    pred, sigma, classif = mix.evaluate(pts, classification=True)
+    assert pred.shape == (300, 2) and sigma.shape == (300, 2)
+    Xs = (X - corners[0]) / (corners[1] - corners[0])
+    ps = (pts - corners[0]) / (corners[1] - corners[0])
+    want_m, want_s = np.empty_like(pred), np.empty_like(sigma)
+    for k in mix.clusters_id:
+        idx = mix.indice_clt[k]
+        sel = classif == k
+        for q in range(2):
+            gp = GaussianProcessRegressor(kernel=kern, normalize_y=True, optimizer=None).fit(Xs[idx], data[idx, q])
+            want_m[sel, q], want_s[sel, q] = gp.predict(ps[sel], return_std=True)
+    np.testing.assert_allclose(pred, want_m, rtol=0, atol=1e-8 * np.abs(want_m).max())
+    np.testing.assert_allclose(sigma ** 2, want_s ** 2, rtol=0, atol=1e-8 * (want_s ** 2).max() + 1e-12)
+    assert (classif == mix.classifier.predict(ps)).all()
+
+
+def test_mixture_docstring_example_runs():
+    """surrogate/mixture.py:11-29 (default clusterer / classifier strings, default local Kriging with DE fits).  The
+    docstring's numbers come from an unseeded KMeans + unseeded DE, so only the contract is asserted."""
+    from batman_b200 import Mixture
+    np.random.seed(123456)
+    samples = np.array([[1., 5.], [2., 5.], [8., 5.], [9., 5.]])
+    data = np.array([[50., 51., 52.], [49., 48., 47.], [10., 11., 12.], [9., 8., 7.]])
+    sample_new = np.array([[0.5, 5.], [10., 5.], [8.5, 5.]])
+    corners = np.array([[1., 5.], [9., 5.]])
+    algo = Mixture(samples, data, corners, 3)
+    pred, sigma = algo.evaluate(sample_new)
+    print(pred, sigma)
+    assert pred.shape == (3, 3) and sigma.shape == (3, 3)
+    assert np.all(np.isfinite(pred)) and np.all(sigma >= 0)
+    with pytest.raises(AttributeError):
+        Mixture(samples, data, corners, 3, clusterer='cluster.NoSuchThing()')

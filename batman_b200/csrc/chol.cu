@@ -179,10 +179,9 @@ __global__ void __launch_bounds__(256, 1) k_gemm_nt(const GemmArgs g) {
 
 static int gemm_nt(const GemmArgs& g, int tiles, int batch, cudaStream_t st) {
     if (tiles <= 0 || batch <= 0) return 0;
-    static bool attr = false;
-    if (!attr) {
+    static OncePerDevice attr;
+    if (attr.first()) {
         BK_CUDA(cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
-        attr = true;
     }
     ProfScope prof(PROF_CHOL, st);
     k_gemm_nt<<<dim3(tiles, batch), 256, G_SMEM, st>>>(g);
@@ -448,11 +447,10 @@ static int side_stream(SideStream** out) {
 static int cholesky_sweep(const LmlWorkspace& w, int n, int R, double* WT, cudaStream_t st) {
     const int n_pad = padded_n(n), nP = n_pad / NB;
     const long mb = (long)n_pad * n_pad, wb = (long)nP * NB * NB;
-    static bool attr = false;
-    if (!attr) {
+    static OncePerDevice attr;
+    if (attr.first()) {
         BK_CUDA(cudaFuncSetAttribute(k_diag_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
         BK_CUDA(cudaFuncSetAttribute(k_diag_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-        attr = true;
     }
     SideStream* ss = nullptr;
     if (int rc = side_stream(&ss)) return rc;
@@ -636,10 +634,9 @@ int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, int8_t* wq_ou
     const int n_pad = padded_n(n), nP = n_pad / NB;
     double* WT = nullptr;
     LmlWorkspace w = carve(ws, n, 1, &WT);
-    static bool attr = false;
-    if (!attr) {
+    static OncePerDevice attr;
+    if (attr.first()) {
         BK_CUDA(cudaFuncSetAttribute(k_diag_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
-        attr = true;
     }
     {
         ProfScope prof(PROF_CHOL, st);

@@ -22,6 +22,19 @@ struct ProfScope {
     ~ProfScope();
 };
 
+// "once per device" latch: function attributes (dynamic shared-memory size) are per device, and one process may
+// drive several GPUs
+struct OncePerDevice {
+    bool done[64] = {};
+    bool first() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 #define BK_CUDA(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return bk::cuda_fail(e__, #call); } while (0)
 #define BK_LAUNCH_CHECK(name) do { cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) return bk::cuda_fail(e__, name); } while (0)
 

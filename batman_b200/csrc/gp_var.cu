@@ -193,10 +193,9 @@ k_var_trmm(const double* __restrict__ wt, const double* __restrict__ kstar, int 
 int launch_var(const bk_gp_s* h, int q, const double* kstar, long k, double* std_out, cudaStream_t st) {
     const GpOutput& o = h->out[q];
     if (!o.wt) return set_error("sigma requested but output %d has no packed L^-1 (w_tiles_dev was NULL)", q);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static OncePerDevice attr_set;
+    if (attr_set.first()) {
         BK_CUDA(cudaFuncSetAttribute(k_var_trmm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VAR_SMEM));
-        attr_set = true;
     }
     const unsigned grid = (unsigned)((k + TILE_T - 1) / TILE_T);
     ProfScope prof(PROF_VAR, st);

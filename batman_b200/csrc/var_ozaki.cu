@@ -366,11 +366,10 @@ int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, doub
                      double* scratch, int* fail_flag, cudaStream_t st) {
     const GpOutput& o = h->out[q];
     if (!o.wq || !o.wsig) return set_error("int8 variance path requested but output %d has no sliced L^-1", q);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static OncePerDevice attr_set;
+    if (attr_set.first()) {
         BK_CUDA(cudaFuncSetAttribute(k_var_ozaki<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
         BK_CUDA(cudaFuncSetAttribute(k_var_ozaki<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
-        attr_set = true;
     }
     const unsigned grid = (unsigned)((k + 127) / 128);
     static int dbg = getenv("BK_OZ_DBG") ? atoi(getenv("BK_OZ_DBG")) : 0;

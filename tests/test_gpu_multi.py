@@ -102,3 +102,28 @@ def test_two_gpu_sharded_restarts_agree_across_ranks():
     ref = GaussianProcessRegressor(kernel=ConstantKernel() * Matern(length_scale=(1.0, 1.0), length_scale_bounds=[(0.01, 100)] * 2),
                                    normalize_y=True, n_restarts_optimizer=20, random_state=0).fit(X, y[:, 0])
     assert res[0][2] >= ref.log_marginal_likelihood_value_ - 1e-3
+
+
+def test_one_process_two_devices():
+    """One process driving two GPUs: function attributes and the side stream are per device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from conftest import kriging_from_states, load_golden
+    from batman_b200 import Kriging
+    from sklearn.gaussian_process import kernels as sk
+    z, states = load_golden('kernel_default_3out')
+    with torch.cuda.device(0):
+        m0, s0 = kriging_from_states(states).evaluate(z['points'])
+    with torch.cuda.device(1):
+        m1, s1 = kriging_from_states(states).evaluate(z['points'])
+        X = states[0]['X_train']
+        y = np.sin(3 * X[:, :1]) + X[:, 1:2]
+        kern = sk.ConstantKernel(1.0, 'fixed') * sk.Matern([0.5] * X.shape[1], 'fixed', nu=1.5)
+        f1 = Kriging(X, y, kernel=kern).evaluate(z['points'])
+    with torch.cuda.device(0):
+        f0 = Kriging(X, y, kernel=kern).evaluate(z['points'])
+    np.testing.assert_array_equal(m0, m1)
+    np.testing.assert_array_equal(s0, s1)
+    np.testing.assert_array_equal(f0[0], f1[0])
+    np.testing.assert_array_equal(f0[1], f1[1])

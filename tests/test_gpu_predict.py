@@ -164,6 +164,32 @@ def test_pickle_roundtrip_drops_device_buffers():
     np.testing.assert_array_equal(s0, s1)
 
 
+def _child_evaluate(blob, pts, q):
+    import pickle
+    k = pickle.loads(blob)
+    q.put(k.evaluate(pts))
+
+
+def test_pickled_model_evaluates_in_a_fresh_process():
+    """SURVEY §8(b) threading note: the reference ships fitted predictors to pool workers (pod.py:366-411,
+    surrogate_model.py:236-258).  CUDA contexts do not survive fork, so device state is created lazily in the
+    process that evaluates; a spawned worker unpickles the model and gets bit-identical results."""
+    import multiprocessing as mp
+    import pickle
+    z, states = load_golden('kernel_default_3out')
+    k = kriging_from_states(states)
+    m0, s0 = k.evaluate(z['points'])
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    proc = ctx.Process(target=_child_evaluate, args=(pickle.dumps(k), z['points'], q))
+    proc.start()
+    m1, s1 = q.get(timeout=300)
+    proc.join(60)
+    assert proc.exitcode == 0
+    np.testing.assert_array_equal(m0, m1)
+    np.testing.assert_array_equal(s0, s1)
+
+
 def test_fit_on_device_reproduces_docstring_and_sklearn_lml():
     """Kriging(...) fits on the device: LML(theta*) must agree with sklearn's LML at the same theta."""
     from batman_b200 import Kriging

@@ -289,7 +289,7 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
         for (int q = 0; q < h->m; ++q) {
             if (h->var_mode >= 1) {
                 const GpOutput& o = h->out[q];
-                const double kappa = pow2_at_least(o.kmax);   // |k| <= |c0| + |c1| (or sum |coef_t|) < kappa
+                const double kappa = pow2_at_least(o.kmax * 1.000001);   // |k| <= (|c0| + |c1| or sum |coef_t|)(1 + few eps) < kappa
                 const int scheme = h->var_mode - 1;
                 if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, nullptr, (int8_t*)kstar,
                                             scheme, kappa, st)) return rc;

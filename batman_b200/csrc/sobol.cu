@@ -354,16 +354,27 @@ static int launch_sobol_general(const bk_gp_s* h, int q, const double* a, const 
     const int p = h->p, nb = sobol_nblocks(p, second), nsums = sobol_nsums(p, second);
     const long SLAB = 1L << 18;                       // base rows per slab: scratch <= 2^18 * (p + nb + 1) doubles
     const long slab_max = count < SLAB ? count : SLAB;
-    double* design = nullptr;
-    double* ybuf = nullptr;
-    double* shift_dev = nullptr;
-    BK_CUDA(cudaMallocAsync(&design, sizeof(double) * slab_max * p, st));
+    struct Scratch {                                   // stream-ordered scratch, released on every exit path
+        cudaStream_t st;
+        double* design = nullptr;
+        double* ybuf = nullptr;
+        double* shift_dev = nullptr;
+        ~Scratch() {
+            if (design) cudaFreeAsync(design, st);
+            if (ybuf) cudaFreeAsync(ybuf, st);
+            if (shift_dev) cudaFreeAsync(shift_dev, st);
+        }
+    } sc{st};
+    BK_CUDA(cudaMallocAsync(&sc.design, sizeof(double) * slab_max * p, st));
     if (!yout) {
-        BK_CUDA(cudaMallocAsync(&ybuf, sizeof(double) * slab_max * nb, st));
-        BK_CUDA(cudaMallocAsync(&shift_dev, sizeof(double), st));
-        BK_CUDA(cudaMemcpyAsync(shift_dev, &shift, sizeof(double), cudaMemcpyHostToDevice, st));
+        BK_CUDA(cudaMallocAsync(&sc.ybuf, sizeof(double) * slab_max * nb, st));
+        BK_CUDA(cudaMallocAsync(&sc.shift_dev, sizeof(double), st));
+        BK_CUDA(cudaMemcpyAsync(sc.shift_dev, &shift, sizeof(double), cudaMemcpyHostToDevice, st));
         BK_CUDA(cudaStreamSynchronize(st));            // `shift` is a stack value
     }
+    double* design = sc.design;
+    double* ybuf = sc.ybuf;
+    double* shift_dev = sc.shift_dev;
     BlockParams bp;
     bp.seed = seed; bp.p = p;
     for (int c = 0; c < MAX_P; ++c) {
@@ -391,9 +402,6 @@ static int launch_sobol_general(const bk_gp_s* h, int q, const double* a, const 
             rc = launch_sobol_y_ex(ybuf, cnt, cnt, p, 1, second, shift_dev, partials + (size_t)q * nsums * 2,
                                    (long)h->m * nsums * 2, st);
     }
-    cudaFreeAsync(design, st);
-    if (ybuf) cudaFreeAsync(ybuf, st);
-    if (shift_dev) cudaFreeAsync(shift_dev, st);
     return rc;
 }
 

@@ -233,3 +233,21 @@ def test_int8_tensor_core_sigma_matches_fp64_path(n, p, kind, ls, scheme):
     err_ld = np.max(np.abs(s1[:32, 0] ** 2 - (sld ** 2).astype(float))) / prior
     print("n=%d %s scheme %d: int8-vs-DMMA %.2e, int8-vs-longdouble %.2e (of the prior variance)" % (n, kind, scheme, err, err_ld))
     assert err <= 1e-11 and err_ld <= RTOL
+
+
+def test_int8_slicing_at_the_top_of_the_covariance_range():
+    """k(x, x) = c reaches the bound the K* slicing is scaled by; with c one ulp below a power of two the scaled
+    value is 1 - 2^-53: the slices must not wrap.  Sigma at and next to training points, int8 vs FP64 kernel."""
+    c = np.nextafter(2.0, 0.0)
+    st = synthetic_state(300, 3, 'matern32', ls=np.full(3, 0.6), c=c)
+    k = kriging_from_states([st])
+    pts = np.vstack([st['X_train'][:64], st['X_train'][:64] + 1e-9, np.random.RandomState(0).rand(200, 3)])
+    model = k._model()
+    model.set_sigma_kernel('dmma')
+    m0, s0 = k.evaluate(pts)
+    for scheme in (0, 1):
+        model.set_int8_scheme(scheme)
+        model.set_sigma_kernel('int8')
+        m1, s1 = k.evaluate(pts)
+        assert np.array_equal(m0, m1)
+        assert np.max(np.abs(s1 ** 2 - s0 ** 2)) <= 1e-12 * c * st['y_std'] ** 2

@@ -1,5 +1,6 @@
 // extern "C" entry points of libbatman_b200.so (declared in include/batman_b200.h).
 #include <math.h>
+#include <stdlib.h>
 #include <stdarg.h>
 
 #include <new>

@@ -322,6 +322,34 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- hyper-parameter fit side of the path, informational: one differential-evolution generation
+    # (15 * (p + 1) = 135 candidates) of log-marginal-likelihood evaluations on this training set, one batched call
+    fit_info = None
+    try:
+        from sklearn.gaussian_process.kernels import ConstantKernel, Matern
+        from batman_b200 import kernel_spec
+        from batman_b200.lml import lml_batched
+        kern = ConstantKernel(CONST) * Matern(length_scale=list(LENGTH_SCALES), nu=1.5)
+        rng = np.random.RandomState(SEED)
+        n_cand = 15 * (P_DIM + 1)
+        specs = [kernel_spec.flatten(kern.clone_with_theta(kern.theta + rng.uniform(-0.5, 0.5, P_DIM + 1)), P_DIM)
+                 for _ in range(n_cand)]
+        Xs_d = torch.from_numpy(np.ascontiguousarray(X)).to(dev)
+        yn = (y[:, 0] - y[:, 0].mean()) / y[:, 0].std()
+        yn_d = torch.from_numpy(np.ascontiguousarray(yn)).to(dev)
+        lml_batched(Xs_d, yn_d, specs)
+        best = 1e9
+        for _ in range(3):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            vals = lml_batched(Xs_d, yn_d, specs)
+            best = min(best, time.perf_counter() - t0)
+        fit_info = {"lml_evaluations_per_s": n_cand / best, "candidates_per_batch": n_cand, "n_train": N_TRAIN,
+                    "ms_per_batch": best * 1e3, "finite": int(np.isfinite(vals).sum()),
+                    "algorithmic_tflops": n_cand * (N_TRAIN ** 3 / 3.0 + 2.0 * N_TRAIN ** 2) / best * 1e-12}
+    except Exception as exc:                        # informational only: never break the bench line
+        fit_info = {"error": repr(exc)}
+
     # ---- roofline of the dominant kernel (gp_var_trmm), live CUDA-event durations on the launching stream
     var_ms, var_launches = ms_arr[1], cnt_arr[1]
     pred_ms, pred_launches = ms_arr[0], cnt_arr[0]
@@ -367,7 +395,8 @@ def main():
             "gpu_launches": int(var_launches + pred_launches), "roofline": roofline,
             "sobol": {"wall_s": float(sob.item()), "N": args.n_base * world, "rows": args.n_base * world * nb,
                       "mean_predictions_per_s": args.n_base * world * nb / float(sob.item()),
-                      "S1": [float(v) for v in indices[1]], "ST": [float(v) for v in indices[2]]}}
+                      "S1": [float(v) for v in indices[1]], "ST": [float(v) for v in indices[2]]},
+            "fit": fit_info}
     if world == 1 and not args.no_cpu_baseline:
         ref = cpu_reference(2, 1, min(args.cpu_sample, R), 1000, host_np)
         line["cpu_baseline"] = {"value": ref['value'], "unit": unit, "cores": ref['cores'], "kind": "port",

@@ -89,6 +89,55 @@ def test_kernel_flatten_general_trees():
         assert spec.nonneg
 
 
+def test_kernel_flatten_random_trees_match_sklearn():
+    """200 random Sum/Product trees over Constant / White / RBF / Matern leaves: the expanded spec either evaluates
+    to sklearn's k(X, Y) and diag(X), or raises NotImplementedError (expansion beyond 3 leaves / 6 terms / power 4)."""
+    rng = np.random.RandomState(7)
+    X, Y = rng.rand(6, 2), rng.rand(5, 2)
+    stat = {kernel_spec.KIND_MATERN12: lambda r: np.exp(-r),
+            kernel_spec.KIND_MATERN32: lambda r: (1 + np.sqrt(3) * r) * np.exp(-np.sqrt(3) * r),
+            kernel_spec.KIND_MATERN52: lambda r: (1 + np.sqrt(5) * r + 5 * r * r / 3) * np.exp(-np.sqrt(5) * r),
+            kernel_spec.KIND_RBF: lambda r: np.exp(-0.5 * r * r),
+            kernel_spec.KIND_MATERN_INF: lambda r: np.exp(-0.5 * r * r)}
+    pool = [lambda: sk.RBF(length_scale=[0.7, 1.3]), lambda: sk.Matern(length_scale=0.9, nu=1.5),
+            lambda: sk.Matern(length_scale=[1.1, 0.4], nu=2.5), lambda: sk.Matern(length_scale=2.0, nu=0.5)]
+
+    def tree(depth):
+        u = rng.rand()
+        if depth == 0 or u < 0.3:
+            v = rng.rand()
+            if v < 0.25:
+                return sk.ConstantKernel(float(rng.uniform(0.2, 3.0)))
+            if v < 0.35:
+                return sk.WhiteKernel(float(rng.uniform(1e-3, 0.5)))
+            return pool[rng.randint(len(pool))]()
+        a, b = tree(depth - 1), tree(depth - 1)
+        return sk.Sum(a, b) if rng.rand() < 0.5 else sk.Product(a, b)
+
+    n_general = n_affine = n_rejected = 0
+    for _ in range(200):
+        k = tree(3)
+        try:
+            spec = kernel_spec.flatten(k, 2)
+        except NotImplementedError:
+            n_rejected += 1
+            continue
+        if spec.general is None:
+            n_affine += 1
+            r = np.sqrt((((X[:, None, :] - Y[None, :, :]) / spec.ls) ** 2).sum(-1))
+            val = spec.c0 + spec.c1 * stat[spec.kind](r)
+        else:
+            n_general += 1
+            g = spec.general
+            assert g.nf <= 3 and g.nt <= 6 and g.texp.max() <= 4
+            fv = [stat[g.fkind[f]](np.sqrt((((X[:, None, :] - Y[None, :, :]) / g.fls[f]) ** 2).sum(-1)))
+                  for f in range(g.nf)]
+            val = sum(g.tcoef[t] * np.prod([fv[f] ** g.texp[t, f] for f in range(g.nf)], axis=0) for t in range(g.nt))
+        np.testing.assert_allclose(val, k(X, Y), rtol=1e-12, atol=1e-14)
+        np.testing.assert_allclose(np.full(6, spec.kdiag), k.diag(X), rtol=1e-14)
+    assert n_general > 20 and n_affine > 20 and n_rejected > 5, (n_general, n_affine, n_rejected)
+
+
 def test_kernel_flatten_rejects_unsupported():
     four = sk.Matern(length_scale=1.0) + sk.RBF(length_scale=2.0) + sk.Matern(length_scale=3.0, nu=0.5) \
         + sk.Matern(length_scale=4.0, nu=2.5)                           # 4 distinct stationary leaves

@@ -46,9 +46,13 @@ class UQ:
 
     def __init__(self, surrogate, dists=None, nsample=1000, method='sobol', indices='aggregated', space=None,
                  data=None, plabels=None, xlabel=None, flabel=None, xdata=None, fname=None, test=None, mesh={},
-                 seed=123456, base_samples=None):
-        """Arguments as uq.py:79-119.  Two additions, both keyword-only in spirit:
+                 seed=123456, base_samples=None, second_order=True):
+        """Arguments as uq.py:79-119.  Three additions, all keyword-only in spirit:
 
+        :param bool second_order: ``True`` (what the reference always does,
+          ``SobolIndicesExperiment(dist, N, True)``, uq.py:331): design with the
+          C blocks, N(2p+2) predictions.  ``False``: first and total order only,
+          N(p+2) predictions, the returned second-order matrix is zero.
         :param int seed: seed of the counter-based base-sample generator
           (batman seeds OpenTURNS with 123456, batman/__init__.py:6).
         :param base_samples: optional ``(A, B)`` arrays (nsample, p) to use instead
@@ -69,6 +73,7 @@ class UQ:
         self.points_sample = nsample
         self.seed = int(seed)
         self.base_samples = base_samples
+        self.second_order = bool(second_order)
         self.dists = dists
         if base_samples is None or surrogate is None:
             try:
@@ -164,10 +169,10 @@ class UQ:
         p = self.p_len
         block = self.type_indices == 'block'
         F = 1 if block else self.output_len
-        second = 1
+        second = 1 if self.second_order else 0
         nsums = lib.bk_sobol_nsums(p, second)
         nslots = lib.bk_sobol_nslots()
-        nb = 2 * p + 2 if p > 2 else p + 2
+        nb = 2 * p + 2 if (p > 2 and second) else p + 2
         dev = torch.device('cuda', torch.cuda.current_device())
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         partials = torch.zeros((nslots, F, nsums, 2), dtype=torch.float64, device=dev)
@@ -233,8 +238,8 @@ class UQ:
             self.logger.info("Created {} samples for Sobol'".format(nb * size))
         else:
             # ensemble mode (uq.py:336-339): user-supplied Saltelli output sample
-            size = len(self.space) // (2 * p + 2)
-            nb_given = 2 * p + 2
+            nb_given = nb                                  # Saltelli sample as written by the driver (uq.py:336-339)
+            size = len(self.space) // nb_given
             Y = torch.from_numpy(np.ascontiguousarray(self.output[:nb_given * size], dtype=np.float64)).to(dev)
             if block:
                 Y = ((Y[:, 1:] + Y[:, :-1]) / 2.0).sum(dim=1, keepdim=True).contiguous()

@@ -299,6 +299,19 @@ def main():
     sob = torch.tensor([min(sob_times)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(sob, op=dist.ReduceOp.MAX)
+    # first and total order only (no C blocks: N(p+2) predictions); the reference always computes second order
+    uq_ft = UQ(surrogate, dists=['Uniform(0., 1.)'] * P_DIM, nsample=args.n_base * world, seed=SEED, second_order=False)
+    uq_ft.sobol()
+    ft_times = []
+    for _ in range(3):
+        barrier()
+        t0 = time.perf_counter()
+        uq_ft.sobol()
+        torch.cuda.synchronize()
+        ft_times.append(time.perf_counter() - t0)
+    sob_ft = torch.tensor([min(ft_times)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(sob_ft, op=dist.ReduceOp.MAX)
 
     # ---- end to end through the public API with host buffers (pinned), copies inside the timed region
     e2e_rows = R
@@ -395,6 +408,7 @@ def main():
             "gpu_launches": int(var_launches + pred_launches), "roofline": roofline,
             "sobol": {"wall_s": float(sob.item()), "N": args.n_base * world, "rows": args.n_base * world * nb,
                       "mean_predictions_per_s": args.n_base * world * nb / float(sob.item()),
+                      "first_total_only_wall_s": float(sob_ft.item()), "first_total_only_rows": args.n_base * world * (P_DIM + 2),
                       "S1": [float(v) for v in indices[1]], "ST": [float(v) for v in indices[2]]},
             "fit": fit_info}
     if world == 1 and not args.no_cpu_baseline:

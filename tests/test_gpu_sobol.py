@@ -244,3 +244,40 @@ def test_pod_inverse_reference_known_answer():
     out = Pod(z['mean_snapshot'], z['U']).inverse_transform(z['modes'])
     np.testing.assert_almost_equal(out, [[40, 43, 41], [41, 47, 42]], decimal=3)
     np.testing.assert_allclose(out, z['ref_inverse'], rtol=0, atol=1e-12)
+
+
+def test_sobol_first_and_total_only():
+    """second_order=False: the design has no C blocks (N(p+2) predictions), centring over the rows that exist;
+    first / total order and Jansen against the oracle on the same base samples; the fused and the POD paths."""
+    from batman_b200 import UQ
+    z, states, s = _surrogate('ishigami_n100')
+    N = 3000
+    dists = [('uniform', -np.pi, np.pi)] * 3
+    A, B = philox.base_samples(123456, 0, N, dists)
+    uq = UQ(s, dists=['Uniform(-3.141592653589793, 3.141592653589793)'] * 3, nsample=N, base_samples=(A, B),
+            second_order=False)
+    s2, s1, st = uq.sobol()
+    Y = _oracle_outputs(z, states, saltelli.design_from_base(A, B, second_order=False))
+    assert Y.shape[0] == 5 * N
+    est = saltelli.saltelli_indices(Y, N, 3, second_order=False)
+    np.testing.assert_allclose(s1, est['S1_agg'], rtol=0, atol=ATOL)
+    np.testing.assert_allclose(st, est['ST_agg'], rtol=0, atol=ATOL)
+    assert np.all(s2 == 0.0)
+    jan = saltelli.jansen_indices(Y, N, 3)
+    np.testing.assert_allclose(uq.details['ST_jansen'], jan['ST'], rtol=0, atol=ATOL)
+    # ensemble mode on the stored p+2 blocks gives the same numbers
+    ens = UQ(None, dists=['Uniform(-3.141592653589793, 3.141592653589793)'] * 3,
+             space=saltelli.design_from_base(A, B, second_order=False), data=Y, second_order=False)
+    e2, e1, et = ens.sobol()
+    np.testing.assert_allclose(e1, s1, rtol=0, atol=ATOL)
+    np.testing.assert_allclose(et, st, rtol=0, atol=ATOL)
+    # POD field path
+    zp, statesp, sp = _surrogate('channel_flow_pod', pod=True)
+    Np = 500
+    Ap, Bp = philox.base_samples(7, 0, Np, [('uniform', 15.0, 60.0), ('normal', 4035.0, 400.0)])
+    g2, g1, gt = UQ(sp, dists=['Uniform(15., 60.)', 'Normal(4035., 400.)'], nsample=Np, base_samples=(Ap, Bp),
+                    second_order=False).sobol()
+    Yp = _oracle_outputs(zp, statesp, saltelli.design_from_base(Ap, Bp, second_order=False), pod=True)
+    estp = saltelli.saltelli_indices(Yp, Np, 2, second_order=False)
+    np.testing.assert_allclose(g1, estp['S1_agg'], rtol=0, atol=ATOL)
+    np.testing.assert_allclose(gt, estp['ST_agg'], rtol=0, atol=ATOL)

@@ -189,7 +189,26 @@ def host_design(n_base, seed=SEED):
     return np.concatenate(blocks, axis=0)
 
 
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    """Exactly ONE line goes to the real stdout (the JSON result).  Everything else that writes to file descriptor 1
+    -- the "NCCL version ..." banner of the first collective, library chatter -- is rerouted to stderr."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    _RESULT_OUT.write(json.dumps(line) + "\n")
+    _RESULT_OUT.flush()
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
@@ -224,7 +243,7 @@ def main():
                                  "sample": ref['sample'], "blas_threads": ref['blas_threads'],
                                  "as_shipped_value": ref['as_shipped_value']},
                 "e2e": {"value": ref['value'], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        _emit(line)
         return
 
     import torch
@@ -416,7 +435,7 @@ def main():
         line["cpu_baseline"] = {"value": ref['value'], "unit": unit, "cores": ref['cores'], "kind": "port",
                                 "sample": ref['sample'], "blas_threads": ref['blas_threads'],
                                 "as_shipped_value": ref['as_shipped_value']}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 

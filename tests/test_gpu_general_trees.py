@@ -156,6 +156,40 @@ def test_general_tree_sobol_vs_oracle_same_design():
     np.testing.assert_allclose(g2, s2, rtol=0, atol=1e-13)
 
 
+def test_general_tree_block_indices_store_path():
+    """indices='block' stores the per-block outputs (bk_sobol_modes) before the trapz reduction: the general
+    composition must fill the same [block][row][output] layout, next to a fast-path output; in-kernel Philox rows
+    beyond one slab (2^18 base rows) exercise the slab loop."""
+    from batman_b200 import SurrogateModel, UQ
+    from oracle import saltelli as osal
+    n, p = 120, 3
+    X = ofun.halton(n, p)
+    Y = np.column_stack([ofun.g_function(X)[:, 0], ofun.ishigami(2 * np.pi * X - np.pi)[:, 0],
+                         np.sin(3 * X[:, 0]) + X[:, 1] * X[:, 2]])
+    trees = [_trees(p)['c*rbf*matern52'], ('prod', ('const', 1.5), ('matern', 1.5, np.full(p, 0.8))),
+             _trees(p)['three leaves']]
+    states = [ogp.fit_state(t, X, Y[:, q]) for q, t in enumerate(trees)]
+    s = SurrogateModel('kriging', np.array([[0.0] * p, [1.0] * p]), None)
+    s.adopt(kriging_from_states(states), X)
+    N = 1000
+    A, B = philox.base_samples(11, 0, N, [('uniform', 0.0, 1.0)] * p)
+    got = UQ(s, dists=['Uniform(0., 1.)'] * p, nsample=N, indices='block', base_samples=(A, B)).sobol()
+    Yd = osal.int_func(ogp.evaluate(states, osal.design_from_base(A, B))[0])
+    want = osal.uq_sobol_aggregate(Yd, N, p, indices='block')
+    for g, w in zip(got, want):
+        np.testing.assert_allclose(g, w, rtol=0, atol=1e-8)
+    # slab loop of the general composition: 300 000 base rows > 2^18, generated in-kernel, vs explicit samples
+    Nbig = 300000
+    one = SurrogateModel('kriging', np.array([[0.0] * p, [1.0] * p]), None)
+    small = ogp.fit_state(_trees(p)['c1*rbf+c2*matern12+white'], X[:32], Y[:32, 0])
+    one.adopt(kriging_from_states([small]), X[:32])
+    Ab, Bb = philox.base_samples(5, 0, Nbig, [('uniform', 0.0, 1.0)] * p)
+    r_gen = UQ(one, dists=['Uniform(0., 1.)'] * p, nsample=Nbig, seed=5).sobol()
+    r_exp = UQ(one, dists=['Uniform(0., 1.)'] * p, nsample=Nbig, base_samples=(Ab, Bb)).sobol()
+    for g, w in zip(r_gen, r_exp):
+        np.testing.assert_allclose(g, w, rtol=0, atol=1e-12)
+
+
 def test_general_tree_limits_raise():
     from batman_b200 import Kriging
     p = 20                                                  # 3 leaves x padded dimension 20 > 48

@@ -187,7 +187,7 @@ class DeviceModel:
                 self.check_pipeline_flag()
         return mean, std
 
-    E2E_CHUNK = 8 * 148 * 128 * 8        # rows per pipelined slice (8 K* chunks)
+    E2E_CHUNK = int(os.environ.get('BATMAN_B200_E2E_CHUNKS', '2')) * 148 * 128 * 8   # rows per pipelined slice (K* chunks of 151 552 rows)
 
     def predict(self, points, return_std=True):
         """numpy in, numpy out (the Kriging.evaluate boundary): host<->device copies included.

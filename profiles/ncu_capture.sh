@@ -4,7 +4,7 @@
 CMD="python bench.py --steps 2 --warmup 1 --n-base 50000 --no-cpu-baseline"
 OUT=gpurun_out
 $CMD > $OUT/plain.log 2>&1 || { echo "plain run failed"; exit 1; }
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1
 for K in k_var_ozaki k_predict k_sobol_static; do
   SKIP=3; [ $K = k_sobol_static ] && SKIP=1
   ncu --set full --clock-control none --import-source on -k regex:$K -s $SKIP -c 1 -f -o /tmp/prof_$K $CMD > $OUT/ncu_$K.log 2>&1

@@ -136,7 +136,7 @@ def measure_dgemm_peak(torch):
 
 def ncu_traffic_bytes(int8=False):
     """DRAM bytes of one launch of the dominant kernel from the committed ncu capture (None if the summary is absent)."""
-    path = os.path.join(ROOT, 'profiles', 'r01_ncu_v4', 'k_var_ozaki_summary.csv') if int8 else \
+    path = os.path.join(ROOT, 'profiles', 'r01_ncu_v5', 'k_var_ozaki_summary.csv') if int8 else \
         os.path.join(ROOT, 'profiles', 'r01_ncu_v2', 'k_var_trmm_summary.csv')
     scale = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
     try:
@@ -408,7 +408,7 @@ def main():
                                 "frac_same_shape": int8_tops / 3249.0,
                                 "peak_source": "profiles/r01_int8_umma_probe.jsonl (tcgen05.mma kind::i8, SMEM operands)"} if int8 else None,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch (151552 points) of the dominant "
-                                  "kernel, ncu --set full capture in profiles/r01_ncu_v4 (int8) or r01_ncu_v2 (dmma); "
+                                  "kernel, ncu --set full capture in profiles/r01_ncu_v5 (int8) or r01_ncu_v2 (dmma); "
                                   "algorithmic bytes per launch = K* chunk + W = %.3e" % (151552 * N_TRAIN * 8 + N_TRAIN * N_TRAIN * 8),
                 "peak_source": "measured live: torch.matmul fp64 8192^3 best of 10 (cuBLAS DGEMM); MEASURED_PEAKS.json "
                                "has no FP64 entry; raw DMMA pipe rate 37.1 TFLOP/s in profiles/r01_fp64_peaks.jsonl",

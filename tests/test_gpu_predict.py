@@ -251,3 +251,45 @@ def test_int8_slicing_at_the_top_of_the_covariance_range():
         m1, s1 = k.evaluate(pts)
         assert np.array_equal(m0, m1)
         assert np.max(np.abs(s1 ** 2 - s0 ** 2)) <= 1e-12 * c * st['y_std'] ** 2
+
+
+def test_c_abi_predict_stays_inside_its_buffers():
+    """bk_gp_predict called directly with canary-framed output and workspace buffers (ragged k, both sigma kernels,
+    a fast-path and a general-tree output): nothing outside [k x m] results and the declared workspace is touched."""
+    import ctypes
+    import torch
+    from batman_b200 import _lib
+    from oracle import functions as ofun
+    lib = _lib.load()
+    p, n = 3, 200
+    X = ofun.halton(n, p)
+    y0 = ofun.g_function(X)[:, 0]
+    y1 = np.sin(3 * X[:, 0]) + X[:, 1] * X[:, 2]
+    ls = np.full(p, 0.7)
+    states = [ogp.fit_state(('prod', ('const', 1.5), ('matern', 1.5, ls)), X, y0),
+              ogp.fit_state(('sum', ('prod', ('const', 1.2), ('rbf', ls)), ('prod', ('const', 0.4), ('matern', 0.5, 2 * ls))), X, y1)]
+    kr = kriging_from_states(states)
+    model = kr._model()
+    model.ensure_w()
+    k, m, pad = 777, 2, 4096
+    pts = torch.rand((k, p), dtype=torch.float64, device='cuda')
+    CAN = -7.25
+    for kernel in ('dmma', 'int8'):
+        model.set_sigma_kernel(kernel)
+        need = lib.bk_gp_predict_workspace(model.handle, k, 1)
+        mean = torch.full((pad + k * m + pad,), CAN, dtype=torch.float64, device='cuda')
+        std = torch.full((pad + k * m + pad,), CAN, dtype=torch.float64, device='cuda')
+        ws = torch.full((need // 8 + 1 + pad,), CAN, dtype=torch.float64, device='cuda')
+        ws[:need // 8 + 1] = 0.0
+        _lib.check(lib.bk_gp_predict(model.handle, ctypes.c_void_p(pts.data_ptr()), k,
+                                     ctypes.c_void_p(mean.data_ptr() + pad * 8), ctypes.c_void_p(std.data_ptr() + pad * 8),
+                                     ctypes.c_void_p(ws.data_ptr()), need, None))
+        torch.cuda.synchronize()
+        for buf in (mean, std):
+            assert bool((buf[:pad] == CAN).all()) and bool((buf[pad + k * m:] == CAN).all())
+            assert not bool((buf[pad:pad + k * m] == CAN).any())
+        assert bool((ws[need // 8 + 1:] == CAN).all())
+        got_m = mean[pad:pad + k * m].reshape(k, m).cpu().numpy()
+        got_s = std[pad:pad + k * m].reshape(k, m).cpu().numpy()
+        om, osd = ogp.evaluate(states, pts.cpu().numpy())
+        _check(got_m, got_s, om, osd, states)

@@ -109,3 +109,57 @@ def test_global_optimizer_finds_at_least_sklearns_optimum():
     # LML at the theta we report must be what sklearn computes at that theta
     assert k.gp_models[0].log_marginal_likelihood_value_ == pytest.approx(
         ref.log_marginal_likelihood(k.gp_models[0].kernel_.theta), rel=1e-8, abs=1e-7)
+
+
+def test_c_abi_lml_and_sobol_stay_inside_their_buffers():
+    """bk_lml_batched / bk_gp_factorise with a canary behind the declared workspace (ragged n: 3 block columns, the
+    split-K partials, the side-stream kernels), bk_sobol_accumulate with a canary behind the partial slots."""
+    import ctypes
+    import torch
+    from batman_b200 import _lib, kernel_spec
+    from batman_b200.fit import normalise_y
+    lib = _lib.load()
+    n, p, R = 300, 4, 5
+    X, y = _data(n, p)
+    yn, _, _ = normalise_y(y)
+    # the C ABI takes dense row-major buffers (scipy's Halton points are Fortran-ordered)
+    Xd, yd = torch.from_numpy(np.ascontiguousarray(X)).cuda(), torch.from_numpy(np.ascontiguousarray(yn)).cuda()
+    kern = ConstantKernel(1.3) * Matern(length_scale=[0.8] * p, nu=1.5)
+    rng = np.random.RandomState(0)
+    specs = [kernel_spec.flatten(kern.clone_with_theta(kern.theta + rng.uniform(-0.5, 0.5, p + 1)), p) for _ in range(R)]
+    CAN, pad = -3.5, 1 << 16
+    need = lib.bk_lml_workspace(n, R, 0)
+    ws = torch.full((need // 8 + 1 + pad,), CAN, dtype=torch.float64, device='cuda')
+    lml = torch.full((R + 64,), CAN, dtype=torch.float64, device='cuda')
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(lib.bk_lml_batched(vp(Xd), vp(yd), n, p, R, _lib.as_int_array([s.kind for s in specs]),
+                                  _lib.as_double_array([s.c0 for s in specs]), _lib.as_double_array([s.c1 for s in specs]),
+                                  _lib.as_double_array([s.kdiag for s in specs]),
+                                  _lib.as_double_array(np.concatenate([s.ls for s in specs])), vp(lml), vp(ws), need, None))
+    torch.cuda.synchronize()
+    assert bool((ws[need // 8 + 1:] == CAN).all()) and bool((lml[R:] == CAN).all())
+    gp = GaussianProcessRegressor(kernel=kern, normalize_y=True, optimizer=None).fit(X, y)
+    want = [gp.log_marginal_likelihood(kern.theta + d) for d in
+            [np.log(np.r_[s.c1, s.ls]) - kern.theta for s in specs]]
+    np.testing.assert_allclose(lml[:R].cpu().numpy(), want, rtol=1e-9, atol=1e-7)
+
+
+def test_c_abi_sobol_partials_canary():
+    import ctypes
+    import torch
+    from conftest import kriging_from_states, load_golden
+    from batman_b200 import _lib
+    lib = _lib.load()
+    z, states = load_golden('kernel_default_3out')
+    model = kriging_from_states(states)._model()
+    p, m = 3, 3
+    nsums, nslots = lib.bk_sobol_nsums(p, 1), lib.bk_sobol_nslots()
+    CAN, pad = -1.75, 4096
+    part = torch.full((nslots * m * nsums * 2 + pad,), CAN, dtype=torch.float64, device='cuda')
+    part[:nslots * m * nsums * 2] = 0.0
+    kinds, params = _lib.as_int_array([0] * p), _lib.as_double_array([0.0, 1.0] * p)
+    _lib.check(lib.bk_sobol_accumulate(model.handle, None, None, 123456, kinds, params, 0, 12345, 1,
+                                       _lib.as_double_array(model.y_means), ctypes.c_void_p(part.data_ptr()), None))
+    torch.cuda.synchronize()
+    assert bool((part[nslots * m * nsums * 2:] == CAN).all())
+    assert bool(torch.isfinite(part[:nslots * m * nsums * 2]).all())

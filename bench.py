@@ -170,8 +170,27 @@ def cpu_reference(steps, warmup, sample_rows, per_point_rows, design_rows):
     k.evaluate(pts[:per_point_rows])
     shipped = per_point_rows / (time.perf_counter() - t0)
     threads = max([i.get('num_threads', 1) for i in threadpool_info()] + [1])
+    # UQ.sobol() on the CPU: mean-only batched predictions over the design + the numpy restatement of
+    # the Saltelli estimator, both on bounded samples and extrapolated linearly to N = 1e6 (R = 1.8e7 rows).  As
+    # shipped the reference predicts mean AND sigma one point at a time and discards sigma (uq.py:192-203).
+    from oracle import saltelli as osal
+    t0 = time.perf_counter()
+    k.evaluate_batched(pts, return_std=False)
+    mean_rate = sample_rows / (time.perf_counter() - t0)
+    n_est = 20000
+    y_est = np.random.RandomState(SEED).rand(n_est * (2 * P_DIM + 2), 1)
+    t0 = time.perf_counter()
+    osal.uq_sobol_aggregate(y_est, n_est, P_DIM)
+    est_s_per_base_row = (time.perf_counter() - t0) / n_est
+    n_full = 1000000
+    rows_full = n_full * (2 * P_DIM + 2)
+    sobol_cpu = {"N": n_full, "rows": rows_full, "mean_only_batched_pred_per_s": mean_rate,
+                 "estimator_s_extrapolated": est_s_per_base_row * n_full,
+                 "wall_s_extrapolated_batched": rows_full / mean_rate + est_s_per_base_row * n_full,
+                 "wall_s_extrapolated_as_shipped": rows_full / shipped + est_s_per_base_row * n_full,
+                 "sample": "%d rows mean-only, estimator on N = %d" % (sample_rows, n_est)}
     return dict(value=sample_rows / float(np.mean(times)), ms_per_step=1e3 * float(np.mean(times)),
-                cores=os.cpu_count(), blas_threads=threads, as_shipped_value=shipped, fit_s=fit_s,
+                cores=os.cpu_count(), blas_threads=threads, as_shipped_value=shipped, fit_s=fit_s, sobol=sobol_cpu,
                 sample="%d design rows per step, sklearn predict(return_std=True) in blocks of 8192 on all host cores; "
                        "as_shipped = kriging.py per-point multi_eval loop on %d rows" % (sample_rows, per_point_rows))
 
@@ -241,7 +260,7 @@ def main():
                 "config": config,
                 "cpu_baseline": {"value": ref['value'], "unit": unit, "cores": ref['cores'], "kind": "port",
                                  "sample": ref['sample'], "blas_threads": ref['blas_threads'],
-                                 "as_shipped_value": ref['as_shipped_value']},
+                                 "as_shipped_value": ref['as_shipped_value'], "sobol": ref['sobol']},
                 "e2e": {"value": ref['value'], "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         _emit(line)
         return
@@ -434,7 +453,7 @@ def main():
         ref = cpu_reference(2, 1, min(args.cpu_sample, R), 1000, host_np)
         line["cpu_baseline"] = {"value": ref['value'], "unit": unit, "cores": ref['cores'], "kind": "port",
                                 "sample": ref['sample'], "blas_threads": ref['blas_threads'],
-                                "as_shipped_value": ref['as_shipped_value']}
+                                "as_shipped_value": ref['as_shipped_value'], "sobol": ref['sobol']}
     _emit(line)
     if world > 1:
         dist.destroy_process_group()

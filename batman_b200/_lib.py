@@ -65,6 +65,7 @@ SIGNATURES = {
     'bk_sobol_accumulate_y': (ctypes.c_int, [vp, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int,
                                              ctypes.c_int, vp, vp, vp]),
     'bk_sobol_reduce_slots': (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, vp, vp]),
+    'bk_sobol_jackknife': (ctypes.c_int, [vp, vp, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]),
     'bk_sobol_result_len': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     'bk_sobol_finalize': (ctypes.c_int, [vp, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]),
 }

@@ -61,6 +61,8 @@ int launch_sobol_y(const double* y, long ld_block, long count, int p, int F, int
 int launch_reduce_slots(const double* partials, int F, int nsums, double* totals, cudaStream_t st);
 int launch_finalize(const double* totals, long N, int p, int F, int second, double* out, cudaStream_t st);
 size_t sobol_result_len(int p, int F);
+int launch_sobol_jackknife(const double* partials, const double* totals, long N, int p, int F, int second, double* out,
+                           cudaStream_t st);
 int launch_debug_fastmath(const double* in, long n, double* o_sqrt, double* o_exp, cudaStream_t st);
 size_t lml_workspace_bytes(int n, int R, bool with_wt);
 int lml_batched(const double* X, const double* y, int n, int p, int R, const int* kinds, const double* c0,
@@ -441,6 +443,13 @@ int bk_sobol_accumulate_y(const double* y_dev, long ld_block, long count, int p,
 int bk_sobol_reduce_slots(const double* partials_dev, int F, int nsums, double* totals_dev, void* stream) {
     if (!partials_dev || !totals_dev) return set_error("bk_sobol_reduce_slots: NULL pointer");
     return launch_reduce_slots(partials_dev, F, nsums, totals_dev, (cudaStream_t)stream);
+}
+
+int bk_sobol_jackknife(const double* partials_dev, const double* totals_dev, long N, int p, int F, int second_order,
+                       double* out_dev, void* stream) {
+    if (!partials_dev || !totals_dev || !out_dev) return set_error("bk_sobol_jackknife: NULL pointer");
+    if (N < 3 || p < 1 || F < 1) return set_error("bk_sobol_jackknife: need N >= 3, p >= 1, F >= 1");
+    return launch_sobol_jackknife(partials_dev, totals_dev, N, p, F, second_order ? 1 : 0, out_dev, (cudaStream_t)stream);
 }
 
 size_t bk_sobol_result_len(int p, int F) { return sobol_result_len(p, F); }

@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(128) k_pod_sobol(const double* __restrict__ ym
                     for (int i = 0; i < p; ++i)
                         for (int j = 0; j < i; ++j) emit8(__dmul_rn(Y(2 + i), Y(2 + p + j)));
                 }
+                emit8(valid ? 1.0 : 0.0);                 // row count
             }
             __syncwarp();
         }

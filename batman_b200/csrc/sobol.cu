@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(SOB_THREADS) k_sobol(const SobolParams<P> prm)
         }
         if (!prm.yout)
             saltelli_products([&](int b) { return y_s[b * SOB_THREADS + tid]; }, prm.p, prm.second, lane,
-                              wsum + (size_t)warp * prm.nsums * 2);
+                              wsum + (size_t)warp * prm.nsums * 2, valid ? 1.0 : 0.0);
     }
     __syncthreads();
     if (!prm.yout)
@@ -272,6 +272,7 @@ __global__ void k_sobol_y(const double* __restrict__ y, long ld_block, long coun
                         for (int j = 0; j < i; ++j) add(__dmul_rn(ys(2 + i), ys(2 + p + j)));
                 }
             }
+            add(1.0);                                    // row count
         }
     }
     __syncthreads();
@@ -532,6 +533,80 @@ __global__ void k_finalize_aggregate(int p, int F, double* __restrict__ out) {
         }
         out[L.S2agg + e] = dd_to_double(dd_div(s2, so));
     }
+}
+
+// ---------------------------------------------------------------- delete-a-group jackknife of the aggregated indices
+// The partial slots are disjoint groups of base rows, so "the estimator without group g" is the estimator of
+// (totals - slot g) with N - n_g rows, n_g = the slot's row count (last sum).  One CTA per slot: threads stride the
+// features, form Var, V_i, VT_i of every feature from the leave-one-group-out sums (same algebra as
+// k_finalize_feature, double-double) and reduce them to the aggregated S_i = sum_f V_i / sum_f Var (uq.py:423-424).
+// out[g] = {active, n_g, S1agg(-g)[p], STagg(-g)[p]}; the host turns these into the jackknife variance.
+__global__ void __launch_bounds__(128) k_sobol_jackknife(const double* __restrict__ partials, const double* __restrict__ totals,
+                                                         long N, int p, int F, int second, int nsums,
+                                                         double* __restrict__ out) {
+    __shared__ double red[4][1 + 2 * MAX_P];
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int width = 2 + 2 * p;
+    const double* P0 = partials + (size_t)g * F * nsums * 2;
+    const double n_g = P0[2 * (nsums - 1)] + P0[2 * (nsums - 1) + 1];
+    const double Nl = (double)N - n_g;                                   // rows left
+    if (!(n_g > 0.0) || Nl < 2.0) {                                      // empty slot (or nothing left): not a group
+        if (tid == 0) { out[(size_t)g * width] = 0.0; out[(size_t)g * width + 1] = n_g; }
+        return;
+    }
+    const int nb = sobol_nblocks(p, second);
+    const dd dN = dd_from(Nl), dN1 = dd_from(Nl - 1.0), dR = dd_from(Nl * nb);
+    const int base2 = 5 + 6 * p;
+    double acc[1 + 2 * MAX_P];
+    for (int i = 0; i < 1 + 2 * p; ++i) acc[i] = 0.0;
+    for (int f = tid; f < F; f += blockDim.x) {
+        const double* T = totals + (size_t)f * nsums * 2;
+        const double* Pg = P0 + (size_t)f * nsums * 2;
+        auto S = [&](int r) { return dd_sub(dd{T[2 * r], T[2 * r + 1]}, dd{Pg[2 * r], Pg[2 * r + 1]}); };
+        dd sum_all = dd_add(S(0), S(1));
+        for (int i = 0; i < p; ++i) sum_all = dd_add(sum_all, S(5 + 6 * i));
+        if (second && p > 2)
+            for (int j = 0; j < p; ++j) sum_all = dd_add(sum_all, S(base2 + 2 * j));
+        const dd delta = dd_div(sum_all, dR);
+        const dd nd2 = dd_mul(dN, dd_mul(delta, delta));
+        auto cdot = [&](dd sxy, dd sx, dd sy) { return dd_add(dd_sub(sxy, dd_mul(delta, dd_add(sx, sy))), nd2); };
+        const dd SA = S(0), SB = S(1);
+        const dd var = dd_div(dd_sub(S(2), dd_div(dd_mul(SA, SA), dN)), dN1);
+        const dd f02 = dd_div(cdot(S(4), SA, SB), dN);
+        const dd muA = dd_sub(dd_div(SA, dN), delta);
+        acc[0] += dd_to_double(var);
+        for (int i = 0; i < p; ++i) {
+            const int b = 5 + 6 * i;
+            const dd SE = S(b);
+            const dd V1 = dd_sub(dd_div(cdot(S(b + 2), SB, SE), dN1), f02);
+            const dd VT = dd_add(dd_sub(var, dd_div(cdot(S(b + 3), SA, SE), dN1)), dd_mul(muA, muA));
+            acc[1 + i] += dd_to_double(V1);
+            acc[1 + p + i] += dd_to_double(VT);
+        }
+    }
+    for (int i = 0; i < 1 + 2 * p; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (tid < 2 * p) {
+        const double sv = red[0][0] + red[1][0] + red[2][0] + red[3][0];
+        const double sn = red[0][1 + tid] + red[1][1 + tid] + red[2][1 + tid] + red[3][1 + tid];
+        out[(size_t)g * width + 2 + tid] = sn / sv;
+    }
+    if (tid == 0) { out[(size_t)g * width] = 1.0; out[(size_t)g * width + 1] = n_g; }
+}
+
+int launch_sobol_jackknife(const double* partials, const double* totals, long N, int p, int F, int second, double* out,
+                           cudaStream_t st) {
+    if (p > MAX_P) return set_error("p = %d exceeds %d", p, MAX_P);
+    const int nsums = sobol_nsums(p, second);
+    ProfScope prof(PROF_OTHER, st);
+    k_sobol_jackknife<<<SOB_SLOTS, 128, 0, st>>>(partials, totals, N, p, F, second, nsums, out);
+    BK_LAUNCH_CHECK("k_sobol_jackknife");
+    return 0;
 }
 
 size_t sobol_result_len(int p, int F) { return finalize_layout(p, F).total; }

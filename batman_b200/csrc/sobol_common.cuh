@@ -28,7 +28,8 @@ constexpr int SOB_CH = 6;         // design blocks evaluated per pass over the t
 constexpr int SOB_SLOTS = 148 * 4;
 
 __host__ __device__ inline int sobol_nsums(int p, int second) {
-    return 5 + 6 * p + ((second && p > 2) ? 2 * p + p * (p - 1) / 2 : 0);
+    // ... + 1: the number of base rows behind the sums (last entry; the delete-a-group jackknife needs it per slot)
+    return 5 + 6 * p + ((second && p > 2) ? 2 * p + p * (p - 1) / 2 : 0) + 1;
 }
 __host__ __device__ inline int sobol_nblocks(int p, int second) { return (second && p > 2) ? 2 * p + 2 : p + 2; }
 
@@ -90,9 +91,10 @@ __device__ __forceinline__ void emit(double v, int& r, int lane, double* wsum_wa
     ++r;
 }
 
-// products of one base row; ys(b) returns the shifted output of block b for this thread's row
+// products of one base row; ys(b) returns the shifted output of block b for this thread's row; one = 1.0 for a
+// real row, 0.0 for a padding thread
 template <typename YS>
-__device__ __forceinline__ void saltelli_products(YS ys, int p, int second, int lane, double* wsum_warp) {
+__device__ __forceinline__ void saltelli_products(YS ys, int p, int second, int lane, double* wsum_warp, double one) {
     int r = 0;
     const double yA = ys(0), yB = ys(1);
     emit(yA, r, lane, wsum_warp);
@@ -122,6 +124,7 @@ __device__ __forceinline__ void saltelli_products(YS ys, int p, int second, int 
         }
         // p == 2: C^0 == E^1 and C^1 == E^0, the product sum(yE^1 yC^0) is sum(yE^1 yE^1): no extra sums
     }
+    emit(one, r, lane, wsum_warp);                        // row count
 }
 
 // CTA epilogue: fixed-order sum of the warps' (hi, lo) sums, ADDED into this CTA's slot

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(SOB_THREADS) k_sobol_static(const SobolParams<
         ss_passes<KIND, P, NLB, 0>(cx, ua, ub);
         if (!prm.yout)
             saltelli_products([&](int b) { return y_s[b * SOB_THREADS + tid]; }, prm.p, prm.second, lane,
-                              wsum + (size_t)warp * prm.nsums * 2);
+                              wsum + (size_t)warp * prm.nsums * 2, cx.valid ? 1.0 : 0.0);
     }
     __syncthreads();
     if (!prm.yout)

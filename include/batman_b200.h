@@ -141,7 +141,7 @@ int bk_tri_inverse_pack(const double* l_dev, int n_train, double* w_tiles_dev, i
 
 /* ---- Saltelli experiment + estimator: replaces ot.SobolIndicesExperiment(...).generate(),
  *      UQ.func over the design, and ot.SaltelliSensitivityAlgorithm (uq/uq.py:331-349,367-375) ---- */
-/* number of accumulated sums per output for input dimension p */
+/* number of accumulated sums per output for input dimension p (the last one is the row count of the slot) */
 int bk_sobol_nsums(int p, int second_order);
 /* number of per-CTA partial slots the accumulate kernel writes */
 int bk_sobol_nslots(void);
@@ -181,6 +181,13 @@ int bk_sobol_accumulate_y(const double* y_dev, long ld_block, long count, int p,
                           void* stream);
 /* fixed-order reduction of the slots: totals_dev [F][nsums][2] (this is what is all-reduced) */
 int bk_sobol_reduce_slots(const double* partials_dev, int F, int nsums, double* totals_dev, void* stream);
+/* Confidence intervals of the aggregated indices: replaces sobol.getFirstOrderIndicesInterval() /
+ * getTotalOrderIndicesInterval() (uq/uq.py:341, 425-426; OpenTURNS' asymptotic intervals) by a delete-a-group jackknife
+ * over the partial slots, which are disjoint groups of base rows.  totals_dev: the GLOBAL totals (after the all-reduce)
+ * of N base rows; partials_dev: this process's slots.  out_dev [nslots][2 + 2p] =
+ * {active (1/0), rows in the group, S1agg without the group [p], STagg without the group [p]}. */
+int bk_sobol_jackknife(const double* partials_dev, const double* totals_dev, long N, int p, int F, int second_order,
+                       double* out_dev, void* stream);
 /* doubles in the packed result of bk_sobol_finalize */
 size_t bk_sobol_result_len(int p, int F);
 /* Estimators from the totals.  out_dev layout (row-major, all double):

@@ -126,6 +126,42 @@ def jansen_indices(Y, N, p):
     return {k: np.asarray(v, dtype=np.float64) for k, v in out.items()}
 
 
+def jackknife_aggregated(Y, N, p, groups, second_order=True):
+    """Delete-a-group jackknife standard errors of the aggregated first / total order indices.
+
+    NOT the reference's estimator: batman asks OpenTURNS for asymptotic (delta-method) intervals
+    (uq/uq.py:341, 425-426), whose formulas cannot be pinned here (module header).  The drop-in reports
+    intervals from a delete-a-group jackknife over disjoint groups of base rows -- asymptotically equivalent
+    for a smooth function of sample means.  ``groups`` is an (N,) array of group ids; groups may differ in
+    size (weights h_g = N / n_g, Busing, Meijer & van der Leeden 1999):
+
+        theta_J  = G theta - sum_g (1 - 1/h_g) theta_(g)
+        var_J    = 1/G sum_g (h_g theta - (h_g - 1) theta_(g) - theta_J)^2 / (h_g - 1)
+
+    Returns (theta (2p,), sigma (2p,)) with theta = [S1_agg, ST_agg]."""
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.ndim == 1:
+        Y = Y[:, None]
+    groups = np.asarray(groups)
+    nb = Y.shape[0] // N
+    full = saltelli_indices(Y, N, p, second_order)
+    theta = np.concatenate([full['S1_agg'], full['ST_agg']])
+    ids = np.unique(groups)
+    G = len(ids)
+    th_g, h = [], []
+    for g in ids:
+        keep = groups != g
+        rows = np.concatenate([np.flatnonzero(keep) + b * N for b in range(nb)])
+        est = saltelli_indices(Y[rows], int(keep.sum()), p, second_order)
+        th_g.append(np.concatenate([est['S1_agg'], est['ST_agg']]))
+        h.append(N / float((~keep).sum()))
+    th_g, h = np.array(th_g), np.array(h)[:, None]
+    theta_j = G * theta - ((1.0 - 1.0 / h) * th_g).sum(axis=0)
+    pseudo = h * theta - (h - 1.0) * th_g
+    var = (((pseudo - theta_j) ** 2) / (h - 1.0)).sum(axis=0) / G
+    return theta, np.sqrt(var)
+
+
 def uq_sobol_aggregate(Y, N, p, indices='aggregated', second_order=True):
     """Return value of ``UQ.sobol()``: [S2, S1, ST]  (uq/uq.py:400-436, 467-471, 499).
 

@@ -281,3 +281,39 @@ def test_sobol_first_and_total_only():
     estp = saltelli.saltelli_indices(Yp, Np, 2, second_order=False)
     np.testing.assert_allclose(g1, estp['S1_agg'], rtol=0, atol=ATOL)
     np.testing.assert_allclose(gt, estp['ST_agg'], rtol=0, atol=ATOL)
+
+
+def test_sobol_intervals_jackknife_vs_oracle_and_files(tmp_path):
+    """95 % intervals of the aggregated indices: device leave-one-group-out estimates (bk_sobol_jackknife over the
+    partial slots; slot of base row k in the fused kernel = (k // 128) % 592) against the numpy jackknife on the same
+    groups; sensitivity.json / sensitivity_aggregated.json in the reference's layout (uq.py:380-393, 437-463)."""
+    import json
+    from batman_b200 import UQ
+    z, states, s = _surrogate('ishigami_n100')
+    N = 20000
+    dists = [('uniform', -np.pi, np.pi)] * 3
+    A, B = philox.base_samples(123456, 0, N, dists)
+    uq = UQ(s, dists=['Uniform(-3.141592653589793, 3.141592653589793)'] * 3, nsample=N, base_samples=(A, B),
+            fname=str(tmp_path), plabels=['x1', 'x2', 'x3'])
+    s2, s1, st = uq.sobol()
+    d = uq.details
+    assert d['jackknife_groups'] == (N + 127) // 128
+    Y = _oracle_outputs(z, states, saltelli.design_from_base(A, B))
+    theta, sigma = saltelli.jackknife_aggregated(Y, N, 3, (np.arange(N) // 128) % 592)
+    np.testing.assert_allclose(np.concatenate([s1, st]), theta, rtol=0, atol=ATOL)
+    np.testing.assert_allclose(np.concatenate([d['S1_agg_sigma'], d['ST_agg_sigma']]), sigma, rtol=1e-6, atol=1e-10)
+    lo, hi = d['S1_interval']
+    assert np.all(lo < s1) and np.all(s1 < hi) and np.all(hi - lo < 0.2)
+    a1, at, _ = ofun.ishigami_indices()
+    agg = json.load(open(tmp_path / 'sensitivity_aggregated.json'))
+    assert list(agg) == [a + lab for a in ['S_min_', 'S_', 'S_max_', 'S_T_min_', 'S_T_', 'S_T_max_'] for lab in ['x1', 'x2', 'x3']]
+    assert agg['S_x1'] == [[s1[0]]] and agg['S_T_max_x3'] == [[d['ST_interval'][1][2]]]
+    sens = json.load(open(tmp_path / 'sensitivity.json'))
+    assert list(sens) == ['S_x1', 'S_x2', 'S_x3', 'S_T_x1', 'S_T_x2', 'S_T_x3'] and sens['S_T_x2'] == [[d['ST'][0, 1]]]
+    # POD field: F = 400 features share the groups; intervals exist and the map file has the x column
+    zp, statesp, sp = _surrogate('channel_flow_pod', pod=True)
+    uqp = UQ(sp, dists=['Uniform(15., 60.)', 'Normal(4035., 400.)'], nsample=3000, fname=str(tmp_path / 'pod'))
+    uqp.sobol()
+    assert np.all(np.isfinite(uqp.details['S1_agg_sigma'])) and uqp.details['jackknife_groups'] > 100
+    m = json.load(open(tmp_path / 'pod' / 'sensitivity.json'))
+    assert list(m)[0] == 'x' and len(m['S_x0']) == sp.pod.mean_snapshot.shape[0]

@@ -27,9 +27,9 @@ def test_library_host_only_queries():
     assert lib.bk_version() >= 100
     assert lib.bk_gp_padded_dim(3) == 4 and lib.bk_gp_padded_dim(8) == 8 and lib.bk_gp_padded_dim(33) == -1
     assert lib.bk_gp_padded_n(100) == 128 and lib.bk_gp_padded_n(1024) == 1024
-    assert lib.bk_sobol_nsums(3, 1) == 5 + 18 + 6 + 3
-    assert lib.bk_sobol_nsums(2, 1) == 5 + 12           # p == 2: C blocks are E blocks
-    assert lib.bk_sobol_nsums(8, 0) == 5 + 48
+    assert lib.bk_sobol_nsums(3, 1) == 5 + 18 + 6 + 3 + 1      # + 1: the row count of the slot
+    assert lib.bk_sobol_nsums(2, 1) == 5 + 12 + 1          # p == 2: C blocks are E blocks
+    assert lib.bk_sobol_nsums(8, 0) == 5 + 48 + 1
     h = ctypes.c_void_p()
     assert lib.bk_gp_create(ctypes.byref(h), 10, 40, 1) != 0      # p too large: error, not a crash
     assert b'dimension' in lib.bk_last_error()

@@ -121,3 +121,28 @@ def test_int_func_is_numpy_trapz():
     trapz = getattr(np, 'trapezoid', None) or np.trapz
     np.testing.assert_allclose(saltelli.int_func(Y)[:, 0], [trapz(r) for r in Y], rtol=1e-15)
     assert np.all(saltelli.int_func(Y[:, :1]) == 0.0)      # scalar output: empty sum (reference behaviour)
+
+
+def test_jackknife_sigma_tracks_the_sampling_spread():
+    """The delete-a-group jackknife standard error of the aggregated indices (what the drop-in reports where the
+    reference reports OpenTURNS' asymptotic intervals) against the empirical spread over independent replications
+    of the experiment (Ishigami, analytic function, N = 2000, 25 groups)."""
+    from oracle import functions as ofun
+    from oracle import philox, saltelli
+    N, p, reps = 2000, 3, 40
+    dists = [('uniform', -np.pi, np.pi)] * p
+    groups = np.arange(N) % 25
+    thetas, sigmas = [], []
+    for r in range(reps):
+        A, B = philox.base_samples(1000 + r, 0, N, dists)
+        Y = ofun.ishigami(saltelli.design_from_base(A, B))
+        if r < 6:
+            th, sg = saltelli.jackknife_aggregated(Y, N, p, groups)
+            sigmas.append(sg)
+        else:
+            est = saltelli.saltelli_indices(Y, N, p)
+            th = np.concatenate([est['S1_agg'], est['ST_agg']])
+        thetas.append(th)
+    spread = np.std(np.array(thetas), axis=0, ddof=1)
+    jk = np.mean(np.array(sigmas), axis=0)
+    assert np.all(jk > 0.55 * spread) and np.all(jk < 1.8 * spread), (jk, spread)

@@ -12,7 +12,7 @@
 // from A) in scipy-cdist order, so 2p+2 distances cost 4P + (2p+2)P DP
 // instructions instead of (2p+2)*3P.  Outputs never reach HBM: per row they
 // are parked in shared memory, multiplied into the (5 + 6p [+ 2p + p(p-1)/2])
-// Saltelli/Jansen products, tree-reduced across the warp with shuffles and
+// Saltelli/Jansen products (plus the row count, the last sum), tree-reduced across the warp with shuffles and
 // accumulated as (hi, lo) double-double sums; each CTA owns one partial slot
 // (no atomics, bit-reproducible for a fixed grid).
 #pragma once

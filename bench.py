@@ -265,6 +265,9 @@ def main():
         _emit(line)
         return
 
+    if not os.path.exists(os.path.join(ROOT, 'batman_b200', 'libbatman_b200.so')) and int(os.environ.get('LOCAL_RANK', '0')) == 0:
+        from batman_b200.csrc import build as _build         # a checkout without the (git-ignored) built library
+        _build.build(force=True)
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)

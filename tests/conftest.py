@@ -14,6 +14,13 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # Safety net for a checkout without the built library (it is git-ignored): compile it once with nvcc.  The
+    # product itself never does this -- batman_b200._lib.load() raises ImportError when the .so is missing.
+    lib = os.path.join(ROOT, 'batman_b200', 'libbatman_b200.so')
+    if not os.path.exists(lib):
+        sys.stderr.write("tests: %s is missing, building it with nvcc (about two minutes)...\n" % lib)
+        from batman_b200.csrc import build as _build
+        _build.build(force=True)
 
 
 def _tree_from_json(node):

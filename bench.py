@@ -265,9 +265,16 @@ def main():
         _emit(line)
         return
 
-    if not os.path.exists(os.path.join(ROOT, 'batman_b200', 'libbatman_b200.so')) and int(os.environ.get('LOCAL_RANK', '0')) == 0:
-        from batman_b200.csrc import build as _build         # a checkout without the (git-ignored) built library
-        _build.build(force=True)
+    lib_path = os.path.join(ROOT, 'batman_b200', 'libbatman_b200.so')
+    if not os.path.exists(lib_path):                         # a checkout without the (git-ignored) built library
+        if int(os.environ.get('LOCAL_RANK', '0')) == 0:
+            from batman_b200.csrc import build as _build
+            _build.build(force=True)
+        else:
+            deadline = time.time() + 900
+            while not os.path.exists(lib_path) and time.time() < deadline:
+                time.sleep(2.0)
+            time.sleep(5.0)                                  # let the linker finish writing
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)

@@ -56,28 +56,39 @@ __device__ __forceinline__ void kstar_write8(const double (&kb)[8], int jg, doub
         for (int a = 0; a < 8; ++a) *reinterpret_cast<uint2*>(d + (size_t)a * 4096) = make_uint2(pk[a][0], pk[a][1]);
     }
     if constexpr (WRITE_K == 3) {
-        // unsigned byte slicing: X = rint(k/kappa * 2^56) in [0, 2^56) = hi * 2^28 + lo; slice b = byte 7-b of X
-        unsigned int pk[7][2];
-#pragma unroll
-        for (int a = 0; a < 7; ++a) pk[a][0] = pk[a][1] = 0u;
+        // unsigned byte slicing: X = rint(k/kappa * 2^56) in [0, 2^56) = hi * 2^32 + lo (hi 24 bits, lo 32 bits, both
+        // byte aligned); slice b = byte 6-b of X.  Two magic-number roundings (no F2I), then the bytes of four
+        // consecutive covariances are gathered with byte permutes (3 PRMT per slice word instead of 16 shift/mask ops:
+        // the kernel is close to issue-slot bound, so integer instructions cost as much as DP ones).
+        unsigned int hi[8], lo[8];
+        const double scale24 = __dmul_rn(inv_kappa, 0x1p24);                              // power of two: exact
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-            const double x28 = __dmul_rn(__dmul_rn(kb[jj], inv_kappa), 0x1p28);
-            const double hm = __dadd_rn(x28, 6755399441055744.0);
-            int hi = __double2loint(hm);                                  // rint(x * 2^28) in [0, 2^28]
-            const double r28 = __dmul_rn(__dadd_rn(x28, -__dadd_rn(hm, -6755399441055744.0)), 0x1p28);
-            int lo = __double2loint(__dadd_rn(r28, 6755399441055744.0));  // in [-2^27, 2^27]
-            if (lo < 0) { lo += 1 << 28; hi -= 1; }                       // 0 <= lo < 2^28
-            if (hi < 0) { hi = 0; lo = 0; }                               // k slightly below 0 by rounding: clamp
-            const unsigned int uh = (unsigned int)hi, ul = (unsigned int)lo;
-            const int sh = 8 * (jj & 3), w = jj >> 2;
-            pk[0][w] |= ((uh >> 20) & 255u) << sh;                        // bits 48..55
-            pk[1][w] |= ((uh >> 12) & 255u) << sh;
-            pk[2][w] |= ((uh >> 4) & 255u) << sh;
-            pk[3][w] |= ((((uh & 15u) << 4) | (ul >> 24)) & 255u) << sh;   // bits 24..31
-            pk[4][w] |= ((ul >> 16) & 255u) << sh;
-            pk[5][w] |= ((ul >> 8) & 255u) << sh;
-            pk[6][w] |= (ul & 255u) << sh;                                // bits 0..7
+            const double x24 = __dmul_rn(kb[jj], scale24);
+            const double hm = __dadd_rn(x24, 6755399441055744.0);
+            int h = __double2loint(hm);                                                   // rint(x * 2^24) in [0, 2^24]
+            const double r32 = __dmul_rn(__dadd_rn(x24, -__dadd_rn(hm, -6755399441055744.0)), 0x1p32);   // [-2^31, 2^31]
+            int l = __double2loint(__dadd_rn(r32, 6755399441055744.0));                   // rint(r32) mod 2^32
+            if (r32 < 0.0) h -= 1;                                                        // borrow: lo = r32 + 2^32
+            if (h < 0) { h = 0; l = 0; }                                                  // k slightly below 0 by rounding: clamp
+            hi[jj] = (unsigned int)h;
+            lo[jj] = (unsigned int)l;
+        }
+        unsigned int pk[7][2];
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+            const unsigned int *H = hi + 4 * w, *L = lo + 4 * w;
+            // byte B of four words -> one word [v0.B | v1.B << 8 | v2.B << 16 | v3.B << 24]
+#define BK_GATHER(V, B) __byte_perm(__byte_perm(V[0], V[1], (B) | ((4 + (B)) << 4)), \
+                                    __byte_perm(V[2], V[3], (B) | ((4 + (B)) << 4)), 0x5410)
+            pk[0][w] = BK_GATHER(H, 2);                                   // bits 48..55
+            pk[1][w] = BK_GATHER(H, 1);
+            pk[2][w] = BK_GATHER(H, 0);                                   // bits 32..39
+            pk[3][w] = BK_GATHER(L, 3);                                   // bits 24..31
+            pk[4][w] = BK_GATHER(L, 2);
+            pk[5][w] = BK_GATHER(L, 1);
+            pk[6][w] = BK_GATHER(L, 0);                                   // bits 0..7
+#undef BK_GATHER
         }
         int8_t* d = qdst + (size_t)(jg >> 5) * 8 * 4096 + ((jg & 31) >> 4) * 128 + (jg & 15);
 #pragma unroll

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(PRED_THREADS) k_predict(const PredictParams<P>
                     double kv = affine(prm.c0, prm.c1, stationary<KIND>(ssum));
                     kbuf[e][jj] = kv;
                     // Kahan: the sum is sign-alternating and badly conditioned
-                    double y = __dadd_rn(__dmul_rn(kv, a), -comp[e]);
+                    double y = __fma_rn(kv, a, -comp[e]);       // product unrounded: the summation order is ours, not sklearn's
                     double tsum = __dadd_rn(acc[e], y);
                     comp[e] = __dadd_rn(__dadd_rn(tsum, -acc[e]), -y);
                     acc[e] = tsum;

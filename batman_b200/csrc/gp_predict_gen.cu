@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(PG_THREADS) k_predict_gen(const PredictGenPara
 #pragma unroll
                     for (int w = 0; w < 8; ++w)
                         if (w == jj) kbuf[e][w] = kv;
-                    const double y = __dadd_rn(__dmul_rn(kv, a), -comp[e]);          // Kahan, as in k_predict
+                    const double y = __fma_rn(kv, a, -comp[e]);                      // Kahan, as in k_predict
                     const double tsum = __dadd_rn(acc[e], y);
                     comp[e] = __dadd_rn(__dadd_rn(tsum, -acc[e]), -y);
                     acc[e] = tsum;

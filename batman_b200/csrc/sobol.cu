@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(SOB_THREADS) k_sobol(const SobolParams<P> prm)
                             for (int c = 0; c < P; ++c)
                                 ssum = __dadd_rn(ssum, ((c == swp[bb]) != fromB[bb]) ? tb[c] : ta[c]);
                             const double kv = affine(prm.c0, prm.c1, stationary<KIND>(ssum));
-                            const double y = __dadd_rn(__dmul_rn(kv, al), -comp[bb]);
+                            const double y = __fma_rn(kv, al, -comp[bb]);
                             const double tsum = __dadd_rn(acc[bb], y);
                             comp[bb] = __dadd_rn(__dadd_rn(tsum, -acc[bb]), -y);
                             acc[bb] = tsum;

@@ -83,7 +83,7 @@ __device__ __forceinline__ void ss_pass(StaticCtx<P>& cx, const double (&ua)[P],
             for (int bb = 0; bb < CNT; ++bb) kv[bb] = affine(prm.c0, prm.c1, stationary<KIND>(kv[bb]));
 #pragma unroll
             for (int bb = 0; bb < CNT; ++bb) {
-                const double y = __dadd_rn(__dmul_rn(kv[bb], al), -comp[bb]);
+                const double y = __fma_rn(kv[bb], al, -comp[bb]);
                 const double tsum = __dadd_rn(acc[bb], y);
                 comp[bb] = __dadd_rn(__dadd_rn(tsum, -acc[bb]), -y);
                 acc[bb] = tsum;

@@ -38,15 +38,16 @@ SIGNATURES = {
     'bk_pack_w': (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
     'bk_gp_predict_workspace': (ctypes.c_size_t, [vp, ctypes.c_long, ctypes.c_int]),
     'bk_gp_predict': (ctypes.c_int, [vp, vp, ctypes.c_long, vp, vp, vp, ctypes.c_size_t, vp]),
+    'bk_gp_predict_status': (ctypes.c_int, [vp, ctypes.c_size_t, c_int_p, vp]),
     'bk_lml_workspace': (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
-    'bk_lml_batched': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, c_double_p, c_double_p,
-                                      c_double_p, c_double_p, vp, vp, ctypes.c_size_t, vp]),
+    'bk_lml_batched': (ctypes.c_int, [vp, vp, ctypes.c_int, c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p,
+                                      c_double_p, c_double_p, c_double_p, c_double_p, vp, vp, ctypes.c_size_t, vp]),
     'bk_gp_factorise': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                        ctypes.c_double, ctypes.c_double, c_double_p, vp, vp, vp, vp, vp, ctypes.c_int,
                                        vp, vp, vp, ctypes.c_size_t, vp]),
-    'bk_lml_batched_general': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p,
-                                              ctypes.c_int, c_int_p, c_double_p, c_double_p, c_double_p, vp, vp,
-                                              ctypes.c_size_t, vp]),
+    'bk_lml_batched_general': (ctypes.c_int, [vp, vp, ctypes.c_int, c_int_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_int, c_int_p, ctypes.c_int, c_int_p, c_double_p, c_double_p,
+                                              c_double_p, vp, vp, ctypes.c_size_t, vp]),
     'bk_gp_factorise_general': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_int_p, ctypes.c_int,
                                                c_int_p, c_double_p, c_double_p, ctypes.c_double, vp, vp, vp, vp, vp,
                                                ctypes.c_int, vp, vp, vp, ctypes.c_size_t, vp]),

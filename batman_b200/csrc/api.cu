@@ -65,16 +65,16 @@ int launch_sobol_jackknife(const double* partials, const double* totals, long N,
                            cudaStream_t st);
 int launch_debug_fastmath(const double* in, long n, double* o_sqrt, double* o_exp, cudaStream_t st);
 size_t lml_workspace_bytes(int n, int R, bool with_wt);
-int lml_batched(const double* X, const double* y, int n, int p, int R, const int* kinds, const double* c0,
-                const double* c1, const double* kdiag, const double* ls, double* lml_out, void* ws, size_t ws_bytes,
-                cudaStream_t st);
+int lml_batched(const double* X, const double* y, int n_targets, const int* target, int n, int p, int R,
+                const int* kinds, const double* c0, const double* c1, const double* kdiag, const double* ls,
+                double* lml_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int gp_factorise(const double* X, const double* y, int n, int p, int kind, double c0, double c1, double kdiag,
                  const double* ls, double* L_out, double* alpha_out, double* wt_tiles_out, int8_t* wq_out,
                  double* wsig_out, int wq_scheme, double* lml_out, int* info_out, void* ws, size_t ws_bytes,
                  cudaStream_t st);
-int lml_batched_general(const double* X, const double* y, int n, int p, int R, int nf, const int* fkind, int nt,
-                        const int* texp, const double* tcoef, const double* fls, const double* kdiag, double* lml_out,
-                        void* ws, size_t ws_bytes, cudaStream_t st);
+int lml_batched_general(const double* X, const double* y, int n_targets, const int* target, int n, int p, int R,
+                        int nf, const int* fkind, int nt, const int* texp, const double* tcoef, const double* fls,
+                        const double* kdiag, double* lml_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int gp_factorise_general(const double* X, const double* y, int n, int p, int nf, const int* fkind, int nt,
                          const int* texp, const double* tcoef, const double* fls, double kdiag, double* L_out,
                          double* alpha_out, double* wt_tiles_out, int8_t* wq_out, double* wsig_out, int wq_scheme,
@@ -287,6 +287,7 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
     double* kstar = (double*)ws;                                               // or the int8 slices: same footprint
     double* scratch = (double*)(ws + (size_t)chunk * h->n_pad * sizeof(double));
     int* fail_flag = (int*)(ws + ((workspace_bytes - 256) & ~(size_t)7));      // tail of the caller's workspace
+    if (h->var_mode >= 1) BK_CUDA(cudaMemsetAsync(fail_flag, 0, sizeof(int), st));   // read back by bk_gp_predict_status
     for (long lo = 0; lo < k; lo += chunk) {
         const long cnt = (k - lo) < chunk ? (k - lo) : chunk;
         for (int q = 0; q < h->m; ++q) {
@@ -307,18 +308,29 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
     return 0;
 }
 
+int bk_gp_predict_status(const void* workspace_dev, size_t workspace_bytes, int* fault_host, void* stream) {
+    if (!workspace_dev || !fault_host) return set_error("bk_gp_predict_status: NULL pointer");
+    if (workspace_bytes < 512) return set_error("bk_gp_predict_status: workspace of %zu bytes has no status tail", workspace_bytes);
+    const char* ws = (const char*)workspace_dev;
+    const int* fail_flag = (const int*)(ws + ((workspace_bytes - 256) & ~(size_t)7));
+    cudaStream_t st = (cudaStream_t)stream;
+    BK_CUDA(cudaMemcpyAsync(fault_host, fail_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    BK_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
 size_t bk_lml_workspace(int n_train, int n_candidates, int with_inverse) {
     return lml_workspace_bytes(n_train, n_candidates, with_inverse != 0);
 }
 
-int bk_lml_batched(const double* x_dev, const double* y_dev, int n_train, int p, int n_candidates,
-                   const int* kind_host, const double* c0_host, const double* c1_host, const double* kdiag_host,
+int bk_lml_batched(const double* x_dev, const double* y_dev, int n_targets, const int* target_host, int n_train, int p,
+                   int n_candidates, const int* kind_host, const double* c0_host, const double* c1_host, const double* kdiag_host,
                    const double* ls_host, double* lml_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
     if (!x_dev || !y_dev || !kind_host || !c0_host || !c1_host || !kdiag_host || !ls_host || !lml_dev || !workspace_dev)
         return set_error("bk_lml_batched: NULL pointer");
     if (n_train < 1 || p < 1 || n_candidates < 1) return set_error("bk_lml_batched: n, p, R must be >= 1");
-    return lml_batched(x_dev, y_dev, n_train, p, n_candidates, kind_host, c0_host, c1_host, kdiag_host, ls_host,
-                       lml_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+    return lml_batched(x_dev, y_dev, n_targets, target_host, n_train, p, n_candidates, kind_host, c0_host, c1_host,
+                       kdiag_host, ls_host, lml_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }
 
 int bk_gp_factorise(const double* x_dev, const double* y_dev, int n_train, int p, int kind, double c0, double c1,
@@ -331,7 +343,8 @@ int bk_gp_factorise(const double* x_dev, const double* y_dev, int n_train, int p
                         wsig_dev, wq_scheme, lml_dev, info_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
 }
 
-int bk_lml_batched_general(const double* x_dev, const double* y_dev, int n_train, int p, int n_candidates, int nf,
+int bk_lml_batched_general(const double* x_dev, const double* y_dev, int n_targets, const int* target_host, int n_train,
+                           int p, int n_candidates, int nf,
                            const int* fkind_host, int nt, const int* texp_host, const double* tcoef_host,
                            const double* fls_host, const double* kdiag_host, double* lml_dev, void* workspace_dev,
                            size_t workspace_bytes, void* stream) {
@@ -340,8 +353,9 @@ int bk_lml_batched_general(const double* x_dev, const double* y_dev, int n_train
     if (n_train < 1 || p < 1 || n_candidates < 1) return set_error("bk_lml_batched_general: n, p, R must be >= 1");
     if (padded_dim(p) < 0) return set_error("bk_lml_batched_general: input dimension %d > %d", p, MAX_P);
     if (int rc = check_general("bk_lml_batched_general", nf, fkind_host, nt, texp_host, padded_dim(p))) return rc;
-    return lml_batched_general(x_dev, y_dev, n_train, p, n_candidates, nf, fkind_host, nt, texp_host, tcoef_host,
-                               fls_host, kdiag_host, lml_dev, workspace_dev, workspace_bytes, (cudaStream_t)stream);
+    return lml_batched_general(x_dev, y_dev, n_targets, target_host, n_train, p, n_candidates, nf, fkind_host, nt,
+                               texp_host, tcoef_host, fls_host, kdiag_host, lml_dev, workspace_dev, workspace_bytes,
+                               (cudaStream_t)stream);
 }
 
 int bk_gp_factorise_general(const double* x_dev, const double* y_dev, int n_train, int p, int nf,

@@ -33,7 +33,7 @@ constexpr double JITTER = 1e-10;   // GaussianProcessRegressor(alpha=1e-10), skl
 // ---------------------------------------------------------------- candidate parameters (device copy)
 struct Cand {
     int kind;
-    int pad_;
+    int target;                       // row of the (n_targets x n) target matrix this candidate is scored on
     double c0, c1, kdiag;
     double ls[MAX_P];
     GenSpec gen;                      // kind == BK_GENERAL
@@ -192,12 +192,13 @@ static int gemm_nt(const GemmArgs& g, int tiles, int batch, cudaStream_t st) {
 // ---------------------------------------------------------------- s = y_k - L[k, <k] z_<k, one warp per row
 // (16 CTAs per candidate instead of a serial prologue inside the single-CTA diagonal-block kernel)
 __global__ void __launch_bounds__(256) k_zdot(const double* __restrict__ M, long m_batch, int ld, int k,
-                                              const double* __restrict__ y, const double* __restrict__ z,
-                                              long z_batch, double* __restrict__ sv) {
+                                              const Cand* __restrict__ cands, const double* __restrict__ ypad,
+                                              const double* __restrict__ z, long z_batch, double* __restrict__ sv) {
     const int r = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i = blockIdx.y * 8 + warp;
     const double* row = M + (size_t)r * m_batch + (size_t)(k * NB + i) * ld;
     const double* zr = z + (size_t)r * z_batch;
+    const double* y = ypad + (size_t)cands[r].target * ld;      // this candidate's (normalised, zero padded) targets
     double part = 0.0;
     for (int j = lane; j < k * NB; j += 32) part = fma(row[j], zr[j], part);     // lanes stride the columns (coalesced)
 #pragma unroll
@@ -361,7 +362,7 @@ size_t lml_workspace_bytes(int n, int R, bool with_wt) {
     b += align_up(sizeof(double) * n_pad * R);                // z
     b += align_up(sizeof(double) * 2 * R);                    // acc
     b += align_up(sizeof(int) * R);                           // info
-    b += align_up(sizeof(double) * n_pad);                    // y padded
+    b += align_up(sizeof(double) * n_pad * R);                // targets, padded (at most one row per candidate)
     b += align_up(sizeof(double) * NB * R);                   // right-hand side of the block forward solve
     b += align_up(sizeof(double) * SPLIT_MAX * NB * NB * R);  // split-K partials of the diagonal block-row update
     if (with_wt) b += align_up(sizeof(double) * n_pad * n_pad * R);
@@ -377,7 +378,7 @@ static LmlWorkspace carve(void* ws, int n, int R, double** wt_out) {
     w.z = (double*)p; p += align_up(sizeof(double) * n_pad * R);
     w.acc = (double*)p; p += align_up(sizeof(double) * 2 * R);
     w.info = (int*)p; p += align_up(sizeof(int) * R);
-    w.ypad = (double*)p; p += align_up(sizeof(double) * n_pad);
+    w.ypad = (double*)p; p += align_up(sizeof(double) * n_pad * R);
     w.sv = (double*)p; p += align_up(sizeof(double) * NB * R);
     w.part = (double*)p; p += align_up(sizeof(double) * SPLIT_MAX * NB * NB * R);
     if (wt_out) *wt_out = (double*)p;
@@ -394,7 +395,7 @@ static int affine_cands(std::vector<Cand>& h, int R, int p, const int* kinds, co
     h.assign(R, Cand());
     for (int r = 0; r < R; ++r) {
         if (kinds[r] < BK_MATERN12 || kinds[r] > BK_MATERN_INF) return set_error("candidate %d: unknown kernel kind %d", r, kinds[r]);
-        h[r].kind = kinds[r]; h[r].pad_ = 0; h[r].c0 = c0[r]; h[r].c1 = c1[r]; h[r].kdiag = kdiag[r];
+        h[r].kind = kinds[r]; h[r].target = 0; h[r].c0 = c0[r]; h[r].c1 = c1[r]; h[r].kdiag = kdiag[r];
         for (int c = 0; c < MAX_P; ++c) h[r].ls[c] = c < p ? ls[(size_t)r * p + c] : 1.0;
     }
     return 0;
@@ -405,7 +406,7 @@ static int general_cands(std::vector<Cand>& h, int R, int p, int nf, const int* 
     h.assign(R, Cand());
     for (int r = 0; r < R; ++r) {
         Cand& cd = h[r];
-        cd.kind = BK_GENERAL; cd.pad_ = 0; cd.c0 = 0.0; cd.c1 = 0.0; cd.kdiag = kdiag[r];
+        cd.kind = BK_GENERAL; cd.target = 0; cd.c0 = 0.0; cd.c1 = 0.0; cd.kdiag = kdiag[r];
         for (int c = 0; c < MAX_P; ++c) cd.ls[c] = 1.0;
         cd.gen.nf = nf; cd.gen.nt = nt;
         for (int f = 0; f < nf; ++f) {
@@ -483,7 +484,7 @@ static int cholesky_sweep(const LmlWorkspace& w, int n, int R, double* WT, cudaS
         BK_CUDA(cudaStreamWaitEvent(ss->s, ss->e_main, 0));
         {
             ProfScope prof(PROF_CHOL, ss->s);
-            k_zdot<<<dim3(R, NB / 8), 256, 0, ss->s>>>(w.M, mb, n_pad, k, w.ypad, w.z, n_pad, w.sv);
+            k_zdot<<<dim3(R, NB / 8), 256, 0, ss->s>>>(w.M, mb, n_pad, k, w.cands, w.ypad, w.z, n_pad, w.sv);
             BK_LAUNCH_CHECK("k_zdot");
             k_diag_block<true><<<R, 256, DIAG_SMEM, ss->s>>>(w.M, mb, n_pad, k, w.Winv, wb, WT, mb, w.sv, w.z, n_pad, w.acc, w.info,
                                                              w.part, nsplit);
@@ -538,22 +539,30 @@ static int build_K(const LmlWorkspace& w, const double* X, int n, int p, int R, 
     return 0;
 }
 
-static int stage_y(const LmlWorkspace& w, const double* y, int n, cudaStream_t st) {
+// y: n_targets x n row-major -> ypad: n_targets x n_pad, zero padded
+static int stage_y(const LmlWorkspace& w, const double* y, int n, int n_targets, cudaStream_t st) {
     const int n_pad = padded_n(n);
-    BK_CUDA(cudaMemsetAsync(w.ypad, 0, sizeof(double) * n_pad, st));
-    BK_CUDA(cudaMemcpyAsync(w.ypad, y, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    BK_CUDA(cudaMemsetAsync(w.ypad, 0, sizeof(double) * n_pad * n_targets, st));
+    BK_CUDA(cudaMemcpy2DAsync(w.ypad, sizeof(double) * n_pad, y, sizeof(double) * n, sizeof(double) * n, n_targets,
+                              cudaMemcpyDeviceToDevice, st));
     return 0;
 }
 
-static int lml_cands(const double* X, const double* y, int n, int p, const std::vector<Cand>& cands, int nf,
-                     double* lml_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+static int lml_cands(const double* X, const double* y, int n_targets, const int* target, int n, int p,
+                     std::vector<Cand>& cands, int nf, double* lml_out, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int R = (int)cands.size();
+    if (n_targets < 1 || n_targets > R) return set_error("bk_lml_batched: n_targets = %d must be in [1, n_candidates = %d]", n_targets, R);
+    for (int r = 0; r < R; ++r) {
+        const int t = target ? target[r] : 0;
+        if (t < 0 || t >= n_targets) return set_error("bk_lml_batched: candidate %d scores target %d of %d", r, t, n_targets);
+        cands[r].target = t;
+    }
     if (p > MAX_P) return set_error("p = %d exceeds %d", p, MAX_P);
     if (ws_bytes < lml_workspace_bytes(n, R, false))
         return set_error("bk_lml_batched: workspace of %zu bytes needed (got %zu)", lml_workspace_bytes(n, R, false), ws_bytes);
     LmlWorkspace w = carve(ws, n, R, nullptr);
     if (int rc = upload_cands(w, cands, st)) return rc;
-    if (int rc = stage_y(w, y, n, st)) return rc;
+    if (int rc = stage_y(w, y, n, n_targets, st)) return rc;
     if (int rc = build_K(w, X, n, p, R, nf, st)) return rc;
     if (int rc = cholesky_sweep(w, n, R, nullptr, st)) return rc;
     k_lml_final<<<(R + 127) / 128, 128, 0, st>>>(w.acc, w.info, n, R, lml_out);
@@ -561,20 +570,20 @@ static int lml_cands(const double* X, const double* y, int n, int p, const std::
     return 0;
 }
 
-int lml_batched(const double* X, const double* y, int n, int p, int R, const int* kinds, const double* c0,
-                const double* c1, const double* kdiag, const double* ls, double* lml_out, void* ws, size_t ws_bytes,
-                cudaStream_t st) {
+int lml_batched(const double* X, const double* y, int n_targets, const int* target, int n, int p, int R,
+                const int* kinds, const double* c0, const double* c1, const double* kdiag, const double* ls,
+                double* lml_out, void* ws, size_t ws_bytes, cudaStream_t st) {
     std::vector<Cand> cands;
     if (int rc = affine_cands(cands, R, p, kinds, c0, c1, kdiag, ls)) return rc;
-    return lml_cands(X, y, n, p, cands, 1, lml_out, ws, ws_bytes, st);
+    return lml_cands(X, y, n_targets, target, n, p, cands, 1, lml_out, ws, ws_bytes, st);
 }
 
-int lml_batched_general(const double* X, const double* y, int n, int p, int R, int nf, const int* fkind, int nt,
-                        const int* texp, const double* tcoef, const double* fls, const double* kdiag, double* lml_out,
-                        void* ws, size_t ws_bytes, cudaStream_t st) {
+int lml_batched_general(const double* X, const double* y, int n_targets, const int* target, int n, int p, int R,
+                        int nf, const int* fkind, int nt, const int* texp, const double* tcoef, const double* fls,
+                        const double* kdiag, double* lml_out, void* ws, size_t ws_bytes, cudaStream_t st) {
     std::vector<Cand> cands;
     if (int rc = general_cands(cands, R, p, nf, fkind, nt, texp, tcoef, fls, kdiag)) return rc;
-    return lml_cands(X, y, n, p, cands, nf, lml_out, ws, ws_bytes, st);
+    return lml_cands(X, y, n_targets, target, n, p, cands, nf, lml_out, ws, ws_bytes, st);
 }
 
 // final state at the chosen theta: L (n_pad x n_pad, row-major lower), alpha (n_pad), packed W tiles, lml, info
@@ -588,7 +597,7 @@ static int factorise_cand(const double* X, const double* y, int n, int p, const 
     double* WT = nullptr;
     LmlWorkspace w = carve(ws, n, 1, &WT);
     if (int rc = upload_cands(w, cand, st)) return rc;
-    if (int rc = stage_y(w, y, n, st)) return rc;
+    if (int rc = stage_y(w, y, n, 1, st)) return rc;
     if (int rc = build_K(w, X, n, p, 1, nf, st)) return rc;
     BK_CUDA(cudaMemsetAsync(WT, 0, sizeof(double) * n_pad * n_pad, st));
     if (int rc = cholesky_sweep(w, n, 1, WT, st)) return rc;

@@ -22,7 +22,8 @@ namespace bk {
 int sobol_nsums_host(int p, int second);
 int sobol_nslots_host();
 
-constexpr int POD_MAX_KSTEPS = 16;   // m <= 64 modes
+constexpr int POD_MAX_KSTEPS = 16;   // m <= 64 modes: the U fragment of a feature tile lives in registers; beyond that
+                                     // (no limit in the reference, pod.py:226-228) it is re-read from L1/L2 per row tile
 
 // ---------------------------------------------------------------- field = mean + modes . U^T
 __global__ void __launch_bounds__(128) k_pod_inverse(const double* __restrict__ modes, long k, int m,
@@ -52,6 +53,11 @@ __global__ void __launch_bounds__(128) k_pod_inverse(const double* __restrict__ 
                     dmma884(c0, c1, a, b[ks]);
                 }
             }
+            for (int ks = POD_MAX_KSTEPS; ks < ksteps; ++ks) {          // m > 64: same order, U from the cache
+                const int q = ks * 4 + tq;
+                const double a = (row < k && q < m) ? modes[(size_t)row * m + q] : 0.0;
+                dmma884(c0, c1, a, (fb < F && q < m) ? U[(size_t)fb * m + q] : 0.0);
+            }
             if (row < k) {
                 if (f0 + 1 < F && (F & 1) == 0) {
                     *reinterpret_cast<double2*>(out + (size_t)row * F + f0) = make_double2(c0, c1);
@@ -66,7 +72,6 @@ __global__ void __launch_bounds__(128) k_pod_inverse(const double* __restrict__ 
 
 int launch_pod_inverse(const double* modes, long k, int m, const double* U, const double* mean, int F, double* out,
                        cudaStream_t st) {
-    if (m > 4 * POD_MAX_KSTEPS) return set_error("bk_pod_inverse: %d modes exceed %d", m, 4 * POD_MAX_KSTEPS);
     if (k <= 0) return 0;
     const int ftiles = (F + 7) / 8;
     const int gy = (ftiles + 3) / 4 < 8 ? (ftiles + 3) / 4 : 8;
@@ -117,6 +122,11 @@ __global__ void __launch_bounds__(128) k_pod_sobol(const double* __restrict__ ym
                         const double a = (valid && q < m) ? src[q] : 0.0;
                         dmma884(c0, c1, a, b[ks]);
                     }
+                }
+                for (int ks = POD_MAX_KSTEPS; ks < ksteps; ++ks) {      // m > 64: same order, U from the cache
+                    const int q = ks * 4 + tq;
+                    const double a = (valid && q < m) ? src[q] : 0.0;
+                    dmma884(c0, c1, a, (fb < F && q < m) ? U[(size_t)fb * m + q] : 0.0);
                 }
                 // shifted outputs of (group g, features f0, f0+1); rows beyond count contribute exact zeros
                 ys[(blk * 32 + lane) * 2 + 0] = valid ? c0 : 0.0;
@@ -173,7 +183,6 @@ __global__ void __launch_bounds__(128) k_pod_sobol(const double* __restrict__ ym
 
 int launch_pod_sobol(const double* ymodes, long count, int p, int m, int second, const double* U, const double* mean,
                      int F, const double* shift, double* partials, cudaStream_t st) {
-    if (m > 4 * POD_MAX_KSTEPS) return set_error("bk_pod_sobol_accumulate: %d modes exceed %d", m, 4 * POD_MAX_KSTEPS);
     if (count <= 0) return 0;
     const int nsums = sobol_nsums_host(p, second);
     const int nb = (second && p > 2) ? 2 * p + 2 : p + 2;

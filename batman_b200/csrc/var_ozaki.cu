@@ -51,10 +51,13 @@ __device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
 __device__ __forceinline__ void oz_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// bounded wait: a mis-programmed pipeline must not hang the GPU box
-__device__ __forceinline__ bool oz_wait(uint64_t* bar, uint32_t parity, int* fail) {
+// bounded wait: a mis-programmed pipeline must not hang the GPU box.  A time-out (or a fault recorded by another
+// role in `fail_s`) makes every later wait of the CTA return at once; callers skip their work but keep walking
+// through their named barriers, so nobody is left blocked.
+__device__ __forceinline__ bool oz_wait(uint64_t* bar, uint32_t parity, int* fail, volatile int* fail_s) {
+    if (*fail) return false;
     for (long spin = 0; !mbar_try_wait(bar, parity); ++spin)
-        if (spin > (1L << 24)) { *fail = 1; return false; }
+        if (spin > (1L << 24) || ((spin & 1023) == 1023 && *fail_s)) { *fail = 1; *fail_s = 1; return false; }
     return true;
 }
 
@@ -98,7 +101,7 @@ template <int SCHEME>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, const int8_t* __restrict__ kq,
             int n_pad, double kappa, double kdiag, double y_std, double* __restrict__ scratch,
-            double* __restrict__ std_out, long k, int ld, int q, int* __restrict__ fail_flag, int dbg) {
+            double* __restrict__ std_out, long k, int ld, int q, int* __restrict__ fail_flag) {
     constexpr int S = OzTraits<SCHEME>::S, BITS = OzTraits<SCHEME>::BITS;
     constexpr int NG1 = OzTraits<SCHEME>::G_END - 6;                 // accumulator groups of pass 1 (4 or 3)
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -110,7 +113,7 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
     uint64_t* acc_full = empty + OZ_SLOTS;
     uint64_t* acc_empty = acc_full + 1;
     __shared__ uint32_t tmem_base_s;
-    __shared__ int fail_s;
+    __shared__ volatile int fail_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_panels = n_pad / 128, nks = n_pad / 32;
@@ -140,9 +143,8 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
             long u = 0;                                                      // running slot-use counter
             auto fill = [&](const int8_t* a_src, uint32_t a_bytes, const int8_t* b_src, uint32_t b_bytes) -> bool {
                 const int s = (int)(u % OZ_SLOTS);
-                if (u >= OZ_SLOTS && !oz_wait(&empty[s], (uint32_t)(((u / OZ_SLOTS) - 1) & 1), &fail)) return false;
+                if (u >= OZ_SLOTS && !oz_wait(&empty[s], (uint32_t)(((u / OZ_SLOTS) - 1) & 1), &fail, &fail_s)) return false;
                 unsigned char* dst = stages + (size_t)s * OZ_SLOT_BYTES;
-                if (dbg & 2) { a_bytes = 16; b_bytes = 0; }                 // timing experiment: no operand traffic
                 mbar_expect_tx(&full[s], a_bytes + b_bytes);
                 tma_load_1d(dst, a_src, a_bytes, &full[s]);
                 if (b_bytes) tma_load_1d(dst + a_bytes, b_src, b_bytes, &full[s]);
@@ -173,13 +175,13 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
             int round = 0;                                                   // (panel, pass) counter
             for (int panel = 0; panel < n_panels && !fail; ++panel)
                 for (int pass = 0; pass < 2 && !fail; ++pass, ++round) {
-                    if (round > 0 && !oz_wait(acc_empty, (uint32_t)((round - 1) & 1), &fail)) break;
+                    if (round > 0 && !oz_wait(acc_empty, (uint32_t)((round - 1) & 1), &fail, &fail_s)) break;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const int nks_p = (panel + 1) * 4;
                     for (int ks = 0; ks < nks_p; ++ks) {
                         const int s0 = (int)(u % OZ_SLOTS), s1 = (int)((u + 1) % OZ_SLOTS);
-                        if (!oz_wait(&full[s0], (uint32_t)((u / OZ_SLOTS) & 1), &fail)) break;
-                        if (pass == 1 && !oz_wait(&full[s1], (uint32_t)(((u + 1) / OZ_SLOTS) & 1), &fail)) break;
+                        if (!oz_wait(&full[s0], (uint32_t)((u / OZ_SLOTS) & 1), &fail, &fail_s)) break;
+                        if (pass == 1 && !oz_wait(&full[s1], (uint32_t)(((u + 1) / OZ_SLOTS) & 1), &fail, &fail_s)) break;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t w_base = smem_u32(stages + (size_t)s0 * OZ_SLOT_BYTES);
                         const uint32_t k_base = pass == 0 ? w_base + 4 * OZ_TILE : smem_u32(stages + (size_t)s1 * OZ_SLOT_BYTES);
@@ -250,44 +252,39 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
                 }
             }
         };
-        for (int panel = 0; panel < n_panels && !fail; ++panel)
-            for (int pass = 0; pass < 2 && !fail; ++pass, ++round) {
+        // After a fault the loop keeps its shape (every epilogue warp meets the named barriers the same number of
+        // times) and only the work is skipped.
+        for (int panel = 0; panel < n_panels; ++panel)
+            for (int pass = 0; pass < 2; ++pass, ++round) {
                 if (pass == 1) {
                     // named barrier among the 8 epilogue warps: previous panel's sigs fully consumed, then refill
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                     if (half == 0) sigs[tp] = wsig[panel * 128 + tp] * kappa;
                     asm volatile("bar.sync 1, 256;" ::: "memory");
                 }
-                if (!oz_wait(acc_full, (uint32_t)(round & 1), &fail)) break;
+                if (!oz_wait(acc_full, (uint32_t)(round & 1), &fail, &fail_s)) continue;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const bool skip = (dbg & 1) || (pass == 0 && (dbg & 4)) || (pass == 1 && (dbg & 8));   // timing experiments
-                if (!skip) {
-                    // 4 chunks of 16 W rows per half, software pipelined: the TMEM read of chunk c+1 flies under the
-                    // arithmetic of chunk c (tcgen05.wait::ld waits for everything issued so far)
-                    const int ng = pass == 0 ? 4 : NG1;
-                    const int c0 = half * 4;
-                    uint32_t da[4][16], db[4][16];
-                    load_chunk(da, c0, ng);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    load_chunk(db, c0 + 1, ng);
-                    process_chunk(da, c0, pass);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    load_chunk(da, c0 + 2, ng);
-                    process_chunk(db, c0 + 1, pass);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    load_chunk(db, c0 + 3, ng);
-                    process_chunk(da, c0 + 2, pass);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    // every TMEM read of this round is complete: release the accumulators before the last arithmetic
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty);
-                    process_chunk(db, c0 + 3, pass);
-                } else {
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(acc_empty);
-                }
+                // 4 chunks of 16 W rows per half, software pipelined: the TMEM read of chunk c+1 flies under the
+                // arithmetic of chunk c (tcgen05.wait::ld waits for everything issued so far)
+                const int ng = pass == 0 ? 4 : NG1;
+                const int c0 = half * 4;
+                uint32_t da[4][16], db[4][16];
+                load_chunk(da, c0, ng);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                load_chunk(db, c0 + 1, ng);
+                process_chunk(da, c0, pass);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                load_chunk(da, c0 + 2, ng);
+                process_chunk(db, c0 + 1, pass);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                load_chunk(db, c0 + 3, ng);
+                process_chunk(da, c0 + 2, pass);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // every TMEM read of this round is complete: release the accumulators before the last arithmetic
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+                process_chunk(db, c0 + 3, pass);
             }
         if (fail) fail_s = 1;
         colred[half * 128 + tp] = vsum;
@@ -372,14 +369,13 @@ int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, doub
         BK_CUDA(cudaFuncSetAttribute(k_var_ozaki<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
     }
     const unsigned grid = (unsigned)((k + 127) / 128);
-    static int dbg = getenv("BK_OZ_DBG") ? atoi(getenv("BK_OZ_DBG")) : 0;
     ProfScope prof(PROF_VAR, st);
     if (scheme == 1)
         k_var_ozaki<1><<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std, scratch,
-                                                          std_out, k, h->m, q, fail_flag, dbg);
+                                                          std_out, k, h->m, q, fail_flag);
     else
         k_var_ozaki<0><<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std, scratch,
-                                                          std_out, k, h->m, q, fail_flag, dbg);
+                                                          std_out, k, h->m, q, fail_flag);
     BK_LAUNCH_CHECK("k_var_ozaki");
     return 0;
 }

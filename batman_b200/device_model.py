@@ -11,7 +11,6 @@ output q (DESIGN.md §"Data layout"):
                 (built lazily: only sigma needs it)
 """
 import ctypes
-import os
 
 import numpy as np
 import torch
@@ -50,10 +49,15 @@ class DeviceModel:
         with torch.cuda.device(self.device):
             Xd = torch.from_numpy(X).to(self.device)
             self.xs, self.alpha = [], []
-            # wts[q] = (FP64 tiles, int8 slices, row scales) of L^-1 when the fit already produced them
-            self.wt = [w[0] if w is not None else None for w in wts] if wts is not None else [None] * self.m
-            self.wq = [w[1] if w is not None else None for w in wts] if wts is not None else [None] * self.m
-            self.wsig = [w[2] if w is not None else None for w in wts] if wts is not None else [None] * self.m
+            # wts[q] = (FP64 tiles, int8 slices, row scales, slicing scheme) of L^-1 when the fit already produced
+            # them.  The sigma kernel uses ONE slicing per model: an output whose fit sliced with the other scheme
+            # (its own coefficients allowed unsigned bytes, another output's do not) is re-sliced by ensure_w().
+            from .lml import int8_scheme
+            self.int8_scheme = int8_scheme(self.n, specs)
+            self.wt, self.wq, self.wsig = [None] * self.m, [None] * self.m, [None] * self.m
+            for q, w in enumerate(wts or []):
+                if w is not None and w[3] == self.int8_scheme:
+                    self.wt[q], self.wq[q], self.wsig[q] = w[0], w[1], w[2]
             for q, spec in enumerate(specs):
                 if spec.general is not None:
                     g = spec.general
@@ -73,17 +77,14 @@ class DeviceModel:
                 self.xs.append(xs)
                 self.alpha.append(al)
                 self._set_output(q)
-        from .lml import int8_scheme
-        self.int8_scheme = int8_scheme(self.n, specs)    # the fit slices L^-1 with the same rule
-        self._forced_scheme = os.environ.get('BATMAN_B200_INT8_SCHEME')
         self._workspace = None
         self._scaler = None
         self.sigma_kernel = 'dmma'
-        # default: the int8 tensor-core kernel (exact slicing, float64-equivalent results, 1.2-1.6x faster);
-        # BATMAN_B200_SIGMA=dmma selects the FP64 DMMA kernel, which also serves n_train > 16384
-        self.set_sigma_kernel(os.environ.get('BATMAN_B200_SIGMA', 'int8' if self.n_pad <= 16384 else 'dmma'))
-        if self._forced_scheme is not None and int(self._forced_scheme) != self.int8_scheme and self._Ls is not None:
-            self.set_int8_scheme(int(self._forced_scheme))
+        # ONE sigma path per model size, no environment switches: the int8 tensor-core kernel (exact slicing,
+        # float64-equivalent results) wherever its int32 accumulation is exact (n_train <= 16384), the FP64 DMMA
+        # kernel above.  set_sigma_kernel / set_int8_scheme remain as explicit calls for the parity tests, which
+        # check both kernels and both slicings against each other.
+        self.set_sigma_kernel('int8' if self.n_pad <= 16384 else 'dmma')
 
     def set_sigma_kernel(self, name):
         """'dmma' = FP64 tensor cores (k_var_trmm); 'int8' = tcgen05 int8 + TMEM, error-free slicing (k_var_ozaki;
@@ -158,16 +159,19 @@ class DeviceModel:
             return None, 0
         if self._workspace is None or self._workspace.numel() * 8 < need:
             self._workspace = torch.empty((need + 7) // 8, dtype=torch.float64, device=self.device)
-            self._workspace[-32:].zero_()             # pipeline-fault flag of k_var_ozaki lives in the tail
         return self._workspace, self._workspace.numel() * 8
 
     def check_pipeline_flag(self):
-        """k_var_ozaki records an mbarrier time-out (a pipeline fault) in the tail of the workspace instead of
-        hanging the GPU; reading it synchronises, so the pipelined host path checks once per call."""
+        """k_var_ozaki records an mbarrier time-out (a pipeline fault) instead of hanging the GPU;
+        ``bk_gp_predict_status`` reads the flag back (it synchronises the stream, so the pipelined host path
+        checks once per call)."""
         ws = self._workspace
-        if ws is not None and self.sigma_kernel == 'int8' and float(ws[-32:].abs().sum().item()) != 0.0:
-            ws[-32:].zero_()
-            raise _lib.BatmanB200Error("k_var_ozaki: an mbarrier wait timed out (pipeline fault)")
+        if ws is None or self.sigma_kernel != 'int8':
+            return
+        fault = ctypes.c_int(0)
+        _lib.check(self.lib.bk_gp_predict_status(_ptr(ws), ws.numel() * 8, ctypes.byref(fault), current_stream_ptr()))
+        if fault.value != 0:
+            raise _lib.BatmanB200Error("k_var_ozaki: an mbarrier wait timed out (pipeline fault); sigma is invalid")
 
     def predict_device(self, pts_dev, return_std=True, check=True):
         """pts_dev: (k, p) float64 CUDA tensor -> (mean, std) CUDA tensors (k, m); std None if not requested."""
@@ -187,7 +191,7 @@ class DeviceModel:
                 self.check_pipeline_flag()
         return mean, std
 
-    E2E_CHUNK = int(os.environ.get('BATMAN_B200_E2E_CHUNKS', '2')) * 148 * 128 * 8   # rows per pipelined slice (K* chunks of 151 552 rows)
+    E2E_CHUNK = 2 * 148 * 128 * 8     # rows per pipelined host slice (two K* chunks of 151 552 rows)
 
     def predict(self, points, return_std=True):
         """numpy in, numpy out (the Kriging.evaluate boundary): host<->device copies included.

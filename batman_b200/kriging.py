@@ -20,6 +20,7 @@ replaced by one batched device call; shapes are the ones ``multi_eval``
 produces: ``(n_points, n_outputs)`` for both mean and sigma, a single 1-D point
 giving ``(1, n_outputs)``.
 """
+import contextlib
 import logging
 
 import numpy as np
@@ -47,7 +48,7 @@ class Kriging:
 
     logger = logging.getLogger(__name__)
 
-    def __init__(self, sample, data, kernel=None, noise=False, global_optimizer=True):
+    def __init__(self, sample, data, kernel=None, noise=False, global_optimizer=True, n_restart=None):
         r"""Create the predictor (arguments as kriging.py:41-76).
 
         :param array_like sample: Sample used to generate the data
@@ -58,6 +59,10 @@ class Kriging:
         :param float/bool noise: Noise used into kriging.
         :param bool global_optimizer: Whether to do global optimization or
           gradient based optimization to estimate hyperparameters.
+        :param int n_restart: (addition) number of differential-evolution
+          restarts; the reference hard-wires 3 (kriging.py:101).  All restarts
+          of all outputs advance in lockstep, one batched device call per
+          generation.
         """
         sample = np.atleast_2d(np.asarray(sample, dtype=np.float64))
         data = np.asarray(data, dtype=np.float64)
@@ -76,7 +81,9 @@ class Kriging:
                 noise = WhiteKernel(noise_level=noise)
             self.kernel += noise
         if global_optimizer:                                             # kriging.py:100-106
-            self.n_restart = 3
+            self.n_restart = 3 if n_restart is None else int(n_restart)
+            if self.n_restart < 1:
+                raise ValueError("n_restart must be >= 1")
             n_local = 0
         else:
             self.n_restart = 1
@@ -92,9 +99,9 @@ class Kriging:
             raise RuntimeError("batman_b200.Kriging needs a CUDA device: there is no CPU fallback")
         X_dev = torch.from_numpy(np.ascontiguousarray(sample)).cuda()
         gps, hyper, wts = [], [], []
-        for q in range(self.model_len):
-            kernel_, _, alpha, L, y_mean, y_std, lml, wt = _fit.fit_output(
-                self.kernel, X_dev, sample, data[:, q], global_optimizer, n_local)
+        fitted, self.fit_stats = _fit.fit_outputs(self.kernel, X_dev, sample, data, global_optimizer, n_local,
+                                                  self.n_restart)
+        for kernel_, _, alpha, L, y_mean, y_std, lml, wt in fitted:
             hyperparameter = np.exp(kernel_.theta)                       # kriging.py:123
             if kernel is None:                                           # kriging.py:126-134
                 hyper_bounds = all([i[0] < j < i[1] for i, j in zip(self.scale_bounds, hyperparameter[1:dim + 1])])
@@ -106,7 +113,6 @@ class Kriging:
         self.gp_models, self.hyperparameter = tuple(gps), tuple(hyper)   # kriging.py:148
         self.logger.debug("Kernels:\n{}".format([gp.kernel_ for gp in self.gp_models]))
         self._device = None
-        self._scaler = None
         self._wts = wts            # packed L^-1 from the fit (device tensors; dropped on pickling)
 
     # ------------------------------------------------------------------ alternate constructors
@@ -130,7 +136,6 @@ class Kriging:
         self.hyperparameter = tuple(np.exp(gp.kernel_.theta) for gp in gps)
         self.n_restart, self.n_cpu = 1, 1
         self._device = None
-        self._scaler = None
         self._wts = None
         return self
 
@@ -146,25 +151,26 @@ class Kriging:
                                        [gp._y_train_mean for gp in self.gp_models],
                                        [gp._y_train_std for gp in self.gp_models],
                                        wts=getattr(self, '_wts', None))
-            if self._scaler is not None:
-                self._device.set_scaler(*self._scaler)
         return self._device
 
-    def set_input_scaler(self, scale, mn):
-        """Fuse ``x*scale + min`` (MinMaxScaler.transform, surrogate_model.py:181) into the kernels,
-        so that raw points can be fed; ``None`` restores ``evaluate``'s own contract (scaled input)."""
-        self._scaler = None if scale is None else (np.asarray(scale, float), np.asarray(mn, float))
-        if self._device is not None:
-            if self._scaler is None:
-                self._device.set_scaler(None, None)
-            else:
-                self._device.set_scaler(*self._scaler)
+    @contextlib.contextmanager
+    def input_scaler(self, scale, mn):
+        """Fuse ``x*scale + min`` (MinMaxScaler.transform, surrogate_model.py:181) into the kernels for the
+        duration of ONE call, so that the facade can feed raw points; on exit the predictor is back to
+        ``evaluate``'s own contract (already-scaled input, kriging.py:192) -- the scaler is never object state."""
+        model = self._model()
+        model.set_scaler(np.asarray(scale, float), np.asarray(mn, float))
+        try:
+            yield model
+        finally:
+            model.set_scaler(None, None)
 
     def __getstate__(self):
         """dill/pickle (surrogate_model.py:271-279): numpy state only, device buffers are rebuilt lazily."""
         state = self.__dict__.copy()
         state['_device'] = None
         state['_wts'] = None
+        state.pop('_scaler', None)          # pickles of the first release carried a sticky scaler
         return state
 
     # ------------------------------------------------------------------ evaluate

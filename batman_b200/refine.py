@@ -67,7 +67,10 @@ class Refiner:
 
         def criterion(x):
             xs = (x - self._lo) / (self._hi - self._lo)
-            d = np.abs(xs[:, None, :] - self.points_scaled[None, :, :]).min(axis=2)      # norm(., -1): min |.|
+            # refiner.py:548-552 takes np.linalg.norm(x_scaled[0][no_discrete] - p[no_discrete], -1) where the index
+            # (None, or a list of lists) makes the operand a 1 x dim MATRIX: ord=-1 is then the smallest column sum
+            # of absolute values, i.e. min_i |dx_i| (not the vector (-1)-norm (sum |dx_i|^-1)^-1).
+            d = np.abs(xs[:, None, :] - self.points_scaled[None, :, :]).min(axis=2)
             too_close = (d < 0.02).any(axis=1)
             pred, sigma = self.pred_sigma(x)
             pred = sign * pred

@@ -147,8 +147,8 @@ class SurrogateModel:
     # ------------------------------------------------------------------ device-level call used by UQ
     def predict_device(self, raw_points_dev, return_std=True):
         """raw (unscaled) points on the device -> (results, sigma) on the device, POD applied."""
-        self.predictor.set_input_scaler(self.scaler.scale_, self.scaler.min_)
-        mean, sigma = self.predictor._model().predict_device(raw_points_dev, return_std)
+        with self.predictor.input_scaler(self.scaler.scale_, self.scaler.min_) as model:
+            mean, sigma = model.predict_device(raw_points_dev, return_std)
         if self.pod is not None:
             mean = self.pod.inverse_transform_device(mean)
             if sigma is not None:
@@ -165,8 +165,8 @@ class SurrogateModel:
                              % (points.shape[1], n_features))
         if self.pod is None:
             # numpy in / numpy out with the copies pipelined against the kernels (DeviceModel.predict)
-            self.predictor.set_input_scaler(self.scaler.scale_, self.scaler.min_)
-            mean, sigma = self.predictor._model().predict(points, return_std=True)
+            with self.predictor.input_scaler(self.scaler.scale_, self.scaler.min_) as model:
+                mean, sigma = model.predict(points, return_std=True)
             return np.atleast_2d(mean), sigma
         pts = torch.from_numpy(np.ascontiguousarray(points)).cuda()
         mean, sigma = self.predict_device(pts, return_std=True)

@@ -46,7 +46,7 @@ class UQ:
 
     def __init__(self, surrogate, dists=None, nsample=1000, method='sobol', indices='aggregated', space=None,
                  data=None, plabels=None, xlabel=None, flabel=None, xdata=None, fname=None, test=None, mesh={},
-                 seed=123456, base_samples=None, second_order=True):
+                 seed=123456, base_samples=None, second_order=True, shard=True):
         """Arguments as uq.py:79-119.  Three additions, all keyword-only in spirit:
 
         :param bool second_order: ``True`` (what the reference always does,
@@ -57,6 +57,10 @@ class UQ:
           (batman seeds OpenTURNS with 123456, batman/__init__.py:6).
         :param base_samples: optional ``(A, B)`` arrays (nsample, p) to use instead
           of the generator (any distribution, any RNG).
+        :param bool shard: with ``torch.distributed`` initialised, split the base
+          rows over the ranks (default); ``False`` keeps the whole experiment on
+          this process' GPU (no collective: what the sharded result is checked
+          against).
         """
         self.logger.info("\n----- UQ module -----")
         self.test = test
@@ -74,6 +78,7 @@ class UQ:
         self.seed = int(seed)
         self.base_samples = base_samples
         self.second_order = bool(second_order)
+        self.shard = bool(shard)
         self.dists = dists
         if base_samples is None or surrogate is None:
             try:
@@ -177,7 +182,7 @@ class UQ:
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         partials = torch.zeros((nslots, F, nsums, 2), dtype=torch.float64, device=dev)
         world, rank = 1, 0
-        if self.surrogate is not None and dist.is_available() and dist.is_initialized():
+        if self.shard and self.surrogate is not None and dist.is_available() and dist.is_initialized():
             world, rank = dist.get_world_size(), dist.get_rank()
 
         def ptr(t):
@@ -194,47 +199,47 @@ class UQ:
                 B_all = torch.from_numpy(np.ascontiguousarray(self.base_samples[1], dtype=np.float64)).to(dev)
                 if A_all.shape != (size, p) or B_all.shape != (size, p):
                     raise ValueError("base_samples must be two (nsample, p) arrays")
-            model = self.surrogate.predictor._model()
             pod = self.surrogate.pod
-            if pod is None and not block:
-                # fused path: design -> mean -> products -> (hi, lo) sums, nothing stored
-                self.surrogate.predictor.set_input_scaler(self.surrogate.scaler.scale_, self.surrogate.scaler.min_)
-                shift = _lib.as_double_array(model.y_means)
-                _lib.check(lib.bk_sobol_accumulate(
-                    model.handle, ptr(A_all[lo:hi]) if A_all is not None else None,
-                    ptr(B_all[lo:hi]) if B_all is not None else None, self.seed, kinds, params, lo, hi - lo,
-                    second, shift, ptr(partials), stream))
-            else:
-                # POD field / block integral: the per-block mode outputs of a chunk of base rows are stored
-                # (bk_sobol_modes), then lifted to the field on the tensor cores and reduced in one kernel
-                # (bk_pod_sobol_accumulate); the N(2p+2) x F output design never exists.
-                self.surrogate.predictor.set_input_scaler(self.surrogate.scaler.scale_, self.surrogate.scaler.min_)
-                m = model.m
-                if pod is not None:
-                    U_h, mean_h = pod.U, pod.mean_snapshot
+            scaler = self.surrogate.scaler
+            # raw design rows go in: the MinMax scaling is fused for this call only (surrogate_model.py:181)
+            with self.surrogate.predictor.input_scaler(scaler.scale_, scaler.min_) as model:
+                if pod is None and not block:
+                    # fused path: design -> mean -> products -> (hi, lo) sums, nothing stored
+                    shift = _lib.as_double_array(model.y_means)
+                    _lib.check(lib.bk_sobol_accumulate(
+                        model.handle, ptr(A_all[lo:hi]) if A_all is not None else None,
+                        ptr(B_all[lo:hi]) if B_all is not None else None, self.seed, kinds, params, lo, hi - lo,
+                        second, shift, ptr(partials), stream))
                 else:
-                    U_h, mean_h = np.eye(m), np.zeros(m)
-                if block:
-                    # np.trapz(f) = sum((f[1:] + f[:-1]) / 2) is linear: integrate the basis once (uq.py:216-217)
-                    w = np.zeros(len(mean_h))
-                    if len(mean_h) > 1:
-                        w[:-1] += 0.5
-                        w[1:] += 0.5
-                    U_h, mean_h = (w @ U_h)[None, :], np.array([w @ mean_h])
-                shift_h = mean_h + U_h @ np.asarray(model.y_means)
-                U_d = torch.from_numpy(np.ascontiguousarray(U_h, dtype=np.float64)).to(dev)
-                mean_d = torch.from_numpy(np.ascontiguousarray(mean_h, dtype=np.float64)).to(dev)
-                shift_d = torch.from_numpy(np.ascontiguousarray(shift_h, dtype=np.float64)).to(dev)
-                chunk = max(1, min(hi - lo, max(1024, int((1 << 26) // max(1, nb * m)))))
-                ymodes = torch.empty(nb * chunk * m, dtype=torch.float64, device=dev)
-                for c0 in range(lo, hi, chunk):
-                    cnt = min(chunk, hi - c0)
-                    _lib.check(lib.bk_sobol_modes(
-                        model.handle, ptr(A_all[c0:c0 + cnt]) if A_all is not None else None,
-                        ptr(B_all[c0:c0 + cnt]) if B_all is not None else None, self.seed, kinds, params, c0, cnt,
-                        second, ptr(ymodes), stream))
-                    _lib.check(lib.bk_pod_sobol_accumulate(ptr(ymodes), cnt, p, m, second, ptr(U_d), ptr(mean_d), F,
-                                                           ptr(shift_d), ptr(partials), stream))
+                    # POD field / block integral: the per-block mode outputs of a chunk of base rows are stored
+                    # (bk_sobol_modes), then lifted to the field on the tensor cores and reduced in one kernel
+                    # (bk_pod_sobol_accumulate); the N(2p+2) x F output design never exists.
+                    m = model.m
+                    if pod is not None:
+                        U_h, mean_h = pod.U, pod.mean_snapshot
+                    else:
+                        U_h, mean_h = np.eye(m), np.zeros(m)
+                    if block:
+                        # np.trapz(f) = sum((f[1:] + f[:-1]) / 2) is linear: integrate the basis once (uq.py:216-217)
+                        w = np.zeros(len(mean_h))
+                        if len(mean_h) > 1:
+                            w[:-1] += 0.5
+                            w[1:] += 0.5
+                        U_h, mean_h = (w @ U_h)[None, :], np.array([w @ mean_h])
+                    shift_h = mean_h + U_h @ np.asarray(model.y_means)
+                    U_d = torch.from_numpy(np.ascontiguousarray(U_h, dtype=np.float64)).to(dev)
+                    mean_d = torch.from_numpy(np.ascontiguousarray(mean_h, dtype=np.float64)).to(dev)
+                    shift_d = torch.from_numpy(np.ascontiguousarray(shift_h, dtype=np.float64)).to(dev)
+                    chunk = max(1, min(hi - lo, max(1024, int((1 << 26) // max(1, nb * m)))))
+                    ymodes = torch.empty(nb * chunk * m, dtype=torch.float64, device=dev)
+                    for c0 in range(lo, hi, chunk):
+                        cnt = min(chunk, hi - c0)
+                        _lib.check(lib.bk_sobol_modes(
+                            model.handle, ptr(A_all[c0:c0 + cnt]) if A_all is not None else None,
+                            ptr(B_all[c0:c0 + cnt]) if B_all is not None else None, self.seed, kinds, params, c0, cnt,
+                            second, ptr(ymodes), stream))
+                        _lib.check(lib.bk_pod_sobol_accumulate(ptr(ymodes), cnt, p, m, second, ptr(U_d), ptr(mean_d), F,
+                                                               ptr(shift_d), ptr(partials), stream))
             self.logger.info("Created {} samples for Sobol'".format(nb * size))
         else:
             # ensemble mode (uq.py:336-339): user-supplied Saltelli output sample

@@ -291,7 +291,6 @@ def main():
     surrogate = SurrogateModel('kriging', corners, None, kernel=fixed_kernel(), global_optimizer=False)
     surrogate.fit(X, y)
     model = surrogate.predictor._model()
-    surrogate.predictor.set_input_scaler(surrogate.scaler.scale_, surrogate.scaler.min_)
     model.ensure_w()
     kinds = _lib.as_int_array([0] * P_DIM)
     params = _lib.as_double_array([0.0, 1.0] * P_DIM)

@@ -103,6 +103,12 @@ size_t bk_gp_predict_workspace(bk_gp_t h, long k, int want_std);
  * row-major.  std_dev may be NULL (mean only). */
 int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, double* std_dev,
                   void* workspace_dev, size_t workspace_bytes, void* stream);
+/* The int8 sigma kernel bounds every mbarrier wait so that a pipeline fault cannot hang the device; a wait that
+ * timed out is recorded in a device-side flag that lives in the LAST 256 bytes of the caller's workspace (zeroed by
+ * bk_gp_predict on `stream` before the kernels run -- callers must not use that tail).  This call waits for `stream`
+ * and returns the flag in *fault_host: 0 = every launch since the last bk_gp_predict completed normally, 1 = sigma
+ * of that call is invalid (the return status of bk_gp_predict cannot carry it: the kernels are asynchronous). */
+int bk_gp_predict_status(const void* workspace_dev, size_t workspace_bytes, int* fault_host, void* stream);
 
 /* ---- hyper-parameter fit: replaces log_marginal_likelihood(theta) (sklearn:_gpr.py:584-617) as driven by
  *      Kriging._optim_evolution / the L-BFGS-B restarts (kriging.py:99-106, 151-190), for R candidates at once,
@@ -110,14 +116,17 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
 /* bytes of workspace for R candidates (with_inverse = 1 adds room for the triangular inverse) */
 size_t bk_lml_workspace(int n_train, int n_candidates, int with_inverse);
 /* lml_dev[r] = LML of k_r(x,x') = c0[r] + c1[r]*stat_kind[r](||(x-x')/ls[r]||), K_ii = kdiag[r] + 1e-10;
- * -inf where the Cholesky fails.  x_dev n x p (scaled design), y_dev n (normalised targets). */
-int bk_lml_batched(const double* x_dev, const double* y_dev, int n_train, int p, int n_candidates,
-                   const int* kind_host, const double* c0_host, const double* c1_host, const double* kdiag_host,
+ * -inf where the Cholesky fails.  x_dev n x p (scaled design).  y_dev is n_targets x n row-major: the normalised
+ * targets of n_targets outputs; candidate r is scored on row target_host[r] (NULL = all on row 0), so that the
+ * populations of ALL restarts (kriging.py:176-181) of ALL outputs (kriging.py:117-143) share one batched call. */
+int bk_lml_batched(const double* x_dev, const double* y_dev, int n_targets, const int* target_host, int n_train, int p,
+                   int n_candidates, const int* kind_host, const double* c0_host, const double* c1_host, const double* kdiag_host,
                    const double* ls_host /* R x p */, double* lml_dev, void* workspace_dev, size_t workspace_bytes,
                    void* stream);
 /* The same for general trees (bk_gp_set_output_general): the tree shape (nf, fkind, nt, texp) is shared by the
  * candidates; tcoef_host is R x nt, fls_host R x nf x p, kdiag_host R. */
-int bk_lml_batched_general(const double* x_dev, const double* y_dev, int n_train, int p, int n_candidates, int nf,
+int bk_lml_batched_general(const double* x_dev, const double* y_dev, int n_targets, const int* target_host, int n_train,
+                           int p, int n_candidates, int nf,
                            const int* fkind_host, int nt, const int* texp_host, const double* tcoef_host,
                            const double* fls_host, const double* kdiag_host, double* lml_dev, void* workspace_dev,
                            size_t workspace_bytes, void* stream);

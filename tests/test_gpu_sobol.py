@@ -167,8 +167,8 @@ def test_sobol_partials_are_additive_over_row_ranges():
     from batman_b200 import _lib
     z, states, s = _surrogate('ishigami_n100')
     lib = _lib.load()
-    s.predictor.set_input_scaler(s.scaler.scale_, s.scaler.min_)
     model = s.predictor._model()
+    model.set_scaler(s.scaler.scale_, s.scaler.min_)      # low-level handle state; the facades set it per call
     p, N = 3, 1000
     nsums, nslots = lib.bk_sobol_nsums(p, 1), lib.bk_sobol_nslots()
     kinds = _lib.as_int_array([0] * p)

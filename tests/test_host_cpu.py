@@ -198,3 +198,70 @@ def test_bench_reference_arm_prints_one_json_line():
         assert key in d, key
     assert d['impl'] == 'reference' and d['value'] > 0 and d['e2e']['h2d_bytes_per_step'] == 0
     assert d['cpu_baseline']['kind'] in ('port', 'reference') and 'sobol' in d['cpu_baseline']
+
+
+def test_lockstep_batcher_batches_all_optimisers_deterministically():
+    """fit.LockstepBatcher: R scipy DE runs in threads, ONE objective batch per generation; the result of each run
+    equals the same run on its own (the batch composition does not depend on thread timing)."""
+    import threading
+    from scipy.optimize import differential_evolution
+    from batman_b200.fit import LockstepBatcher
+    bounds = np.array([[-3.0, 3.0]] * 3)
+    centres = {c: np.array([0.5 * c, -0.25 * c, 0.1]) for c in range(5)}
+
+    def f(cid, pts):                                   # pts (S, d) -> (S,)
+        return ((pts - centres[cid]) ** 2).sum(axis=1) + 0.1 * np.sin(5 * pts).sum(axis=1)
+
+    sizes = []
+
+    def evaluate(batch):
+        sizes.append(sum(len(t) for _, t in batch))
+        assert [c for c, _ in batch] == sorted(c for c, _ in batch)
+        return [f(cid, t) for cid, t in batch]
+
+    def run(cid, fun):
+        return differential_evolution(lambda th: fun(th.T), bounds, tol=1e-3, popsize=8 + cid, vectorized=True,
+                                      updating='deferred', polish=False, seed=100 + cid, maxiter=40)
+
+    batcher = LockstepBatcher(evaluate, list(centres))
+    results = {}
+
+    def work(cid):
+        try:
+            results[cid] = run(cid, lambda pts: batcher.submit(cid, pts))
+        finally:
+            batcher.retire(cid)
+    threads = [threading.Thread(target=work, args=(c,)) for c in centres]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert len(results) == 5
+    for cid in centres:
+        alone = run(cid, lambda pts: f(cid, pts))
+        np.testing.assert_array_equal(results[cid].x, alone.x)
+        assert results[cid].nfev == alone.nfev
+    # the first batches carry all five populations: 3 * (8+9+10+11+12) candidates
+    assert sizes[0] == 3 * sum(8 + c for c in centres)
+    assert batcher.n_batches == len(sizes) and batcher.n_evals == sum(sizes)
+    assert batcher.n_batches <= max(r.nit for r in results.values()) + 2
+
+
+def test_lockstep_batcher_propagates_failures_without_deadlock():
+    import threading
+    from batman_b200.fit import LockstepBatcher
+
+    def evaluate(batch):
+        raise ValueError("device fault")
+    batcher = LockstepBatcher(evaluate, [0, 1])
+    errs = []
+
+    def work(cid):
+        try:
+            batcher.submit(cid, np.zeros((2, 2)))
+        except RuntimeError as exc:
+            errs.append(exc)
+        finally:
+            batcher.retire(cid)
+    threads = [threading.Thread(target=work, args=(c,)) for c in (0, 1)]
+    [t.start() for t in threads]
+    [t.join(timeout=20) for t in threads]
+    assert len(errs) == 2 and all(isinstance(e.__cause__, ValueError) for e in errs)

@@ -380,15 +380,19 @@ int bk_tri_inverse_pack(const double* l_dev, int n_train, double* w_tiles_dev, i
                             (cudaStream_t)stream);
 }
 
+static int check_marginals(const char* who, int p, const int* kind) {
+    for (int c = 0; c < p; ++c)
+        if (kind[c] < 0 || kind[c] >= BK_MARGINAL_COUNT) return set_error("%s: marginal %d has unknown kind %d", who, c, kind[c]);
+    return 0;
+}
+
 int bk_sobol_nsums(int p, int second_order) { return sobol_nsums_host(p, second_order); }
 int bk_sobol_nslots(void) { return sobol_nslots_host(); }
 
 int bk_design_rows(uint64_t seed, long row_lo, long count, int p, const int* marg_kind_host,
                    const double* marg_par_host, int stream_id, double* out_dev, void* stream) {
     if (!marg_kind_host || !marg_par_host || !out_dev) return set_error("bk_design_rows: NULL pointer");
-    for (int c = 0; c < p; ++c)
-        if (marg_kind_host[c] != BK_UNIFORM && marg_kind_host[c] != BK_NORMAL)
-            return set_error("bk_design_rows: marginal %d has unknown kind %d", c, marg_kind_host[c]);
+    if (int rc = check_marginals("bk_design_rows", p, marg_kind_host)) return rc;
     return launch_design_rows(seed, row_lo, count, p, marg_kind_host, marg_par_host, stream_id, out_dev,
                               (cudaStream_t)stream);
 }
@@ -401,9 +405,7 @@ int bk_sobol_accumulate(bk_gp_t h, const double* a_dev, const double* b_dev, uin
     if (!a_dev && (!marg_kind_host || !marg_par_host))
         return set_error("bk_sobol_accumulate: no base samples and no marginals to generate them from");
     if (!a_dev)
-        for (int c = 0; c < h->p; ++c)
-            if (marg_kind_host[c] != BK_UNIFORM && marg_kind_host[c] != BK_NORMAL)
-                return set_error("bk_sobol_accumulate: marginal %d has unknown kind %d", c, marg_kind_host[c]);
+        if (int rc = check_marginals("bk_sobol_accumulate", h->p, marg_kind_host)) return rc;
     if (count <= 0) return 0;
     for (int q = 0; q < h->m; ++q)
         if (int rc = launch_sobol(h, q, a_dev, b_dev, seed, marg_kind_host, marg_par_host, row_lo, count,
@@ -420,6 +422,8 @@ int bk_sobol_modes(bk_gp_t h, const double* a_dev, const double* b_dev, uint64_t
     if ((a_dev == nullptr) != (b_dev == nullptr)) return set_error("bk_sobol_modes: a_dev and b_dev must both be given or both NULL");
     if (!a_dev && (!marg_kind_host || !marg_par_host))
         return set_error("bk_sobol_modes: no base samples and no marginals to generate them from");
+    if (!a_dev)
+        if (int rc = check_marginals("bk_sobol_modes", h->p, marg_kind_host)) return rc;
     if (count <= 0) return 0;
     for (int q = 0; q < h->m; ++q)
         if (int rc = launch_sobol(h, q, a_dev, b_dev, seed, marg_kind_host, marg_par_host, row_lo, count,

@@ -9,15 +9,14 @@ struct DesignParams {
     uint64_t seed;
     long row_lo, count;
     int p, stream;
-    int kind[MAX_P];
-    double pa[MAX_P], pb[MAX_P];
+    MargPar<MAX_P> marg;
     double* out;
 };
 __global__ void k_design_rows(const DesignParams prm) {
     const long g = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= prm.count) return;
     double x[MAX_P];
-    design_row<MAX_P>(prm.seed, (uint64_t)(prm.row_lo + g), prm.p, prm.stream, prm.kind, prm.pa, prm.pb, x);
+    design_row<MAX_P>(prm.seed, (uint64_t)(prm.row_lo + g), prm.p, prm.stream, prm.marg, x);
     for (int c = 0; c < prm.p; ++c) prm.out[g * prm.p + c] = x[c];
 }
 
@@ -70,8 +69,8 @@ __global__ void __launch_bounds__(SOB_THREADS) k_sobol(const SobolParams<P> prm)
                     xb[c] = c < prm.p ? prm.b[gc * prm.p + c] : 0.0;
                 }
             } else {
-                design_row<P>(prm.seed, (uint64_t)(prm.row_lo + gc), prm.p, 0, prm.mkind, prm.mpa, prm.mpb, xa);
-                design_row<P>(prm.seed, (uint64_t)(prm.row_lo + gc), prm.p, 1, prm.mkind, prm.mpa, prm.mpb, xb);
+                design_row<P>(prm.seed, (uint64_t)(prm.row_lo + gc), prm.p, 0, prm.marg, xa);
+                design_row<P>(prm.seed, (uint64_t)(prm.row_lo + gc), prm.p, 1, prm.marg, xb);
             }
 #pragma unroll
             for (int c = 0; c < P; ++c) {
@@ -159,10 +158,8 @@ static int launch_sobol_kp(const bk_gp_s* h, int q, const double* a, const doubl
     const GpOutput& o = h->out[q];
     SobolParams<P> prm;
     prm.a = a; prm.b = b; prm.seed = seed;
+    marg_fill<P>(prm.marg, h->p, mkind, mpar);
     for (int c = 0; c < P; ++c) {
-        prm.mkind[c] = (c < h->p && mkind) ? mkind[c] : 0;
-        prm.mpa[c] = (c < h->p && mpar) ? mpar[2 * c] : 0.0;
-        prm.mpb[c] = (c < h->p && mpar) ? mpar[2 * c + 1] : 0.0;
         prm.scale[c] = c < h->p ? h->scale[c] : 0.0;
         prm.mn[c] = c < h->p ? h->mn[c] : 0.0;
         prm.ls[c] = c < h->p ? o.ls[c] : 1.0;
@@ -221,11 +218,7 @@ int launch_design_rows(uint64_t seed, long row_lo, long count, int p, const int*
     if (p > MAX_P) return set_error("p = %d exceeds %d", p, MAX_P);
     DesignParams prm;
     prm.seed = seed; prm.row_lo = row_lo; prm.count = count; prm.p = p; prm.stream = stream_id; prm.out = out;
-    for (int c = 0; c < MAX_P; ++c) {
-        prm.kind[c] = c < p ? mkind[c] : 0;
-        prm.pa[c] = c < p ? mpar[2 * c] : 0.0;
-        prm.pb[c] = c < p ? mpar[2 * c + 1] : 0.0;
-    }
+    marg_fill<MAX_P>(prm.marg, p, mkind, mpar);
     if (count <= 0) return 0;
     k_design_rows<<<(unsigned)((count + 127) / 128), 128, 0, st>>>(prm);
     BK_LAUNCH_CHECK("k_design_rows");
@@ -326,8 +319,7 @@ struct BlockParams {
     uint64_t seed;
     long row_lo, count;
     int p, block;          // block: 0 = A, 1 = B, 2+i = E^i, 2+p+i = C^i
-    int kind[MAX_P];
-    double pa[MAX_P], pb[MAX_P];
+    MargPar<MAX_P> marg;
     double* out;           // count x p
 };
 __global__ void k_design_block(const BlockParams prm) {
@@ -340,8 +332,8 @@ __global__ void k_design_block(const BlockParams prm) {
     if (prm.a) {
         for (int c = 0; c < p; ++c) { xa[c] = prm.a[g * p + c]; xb[c] = prm.b[g * p + c]; }
     } else {
-        design_row<MAX_P>(prm.seed, (uint64_t)(prm.row_lo + g), p, 0, prm.kind, prm.pa, prm.pb, xa);
-        design_row<MAX_P>(prm.seed, (uint64_t)(prm.row_lo + g), p, 1, prm.kind, prm.pa, prm.pb, xb);
+        design_row<MAX_P>(prm.seed, (uint64_t)(prm.row_lo + g), p, 0, prm.marg, xa);
+        design_row<MAX_P>(prm.seed, (uint64_t)(prm.row_lo + g), p, 1, prm.marg, xb);
     }
     for (int c = 0; c < p; ++c) prm.out[g * p + c] = ((c == swp) != fromB) ? xb[c] : xa[c];
 }
@@ -378,11 +370,7 @@ static int launch_sobol_general(const bk_gp_s* h, int q, const double* a, const 
     double* shift_dev = sc.shift_dev;
     BlockParams bp;
     bp.seed = seed; bp.p = p;
-    for (int c = 0; c < MAX_P; ++c) {
-        bp.kind[c] = (c < p && mkind) ? mkind[c] : 0;
-        bp.pa[c] = (c < p && mpar) ? mpar[2 * c] : 0.0;
-        bp.pb[c] = (c < p && mpar) ? mpar[2 * c + 1] : 0.0;
-    }
+    marg_fill<MAX_P>(bp.marg, p, mkind, mpar);
     int rc = 0;
     for (long lo = 0; lo < count && rc == 0; lo += SLAB) {
         const long cnt = (count - lo) < SLAB ? (count - lo) : SLAB;

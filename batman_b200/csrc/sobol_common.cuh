@@ -49,23 +49,131 @@ __device__ __forceinline__ double unit_from_words(uint32_t hi, uint32_t lo) {
     const uint64_t k = ((uint64_t)(hi >> 6) << 26) | (uint64_t)(lo >> 6);
     return __dmul_rn(__dadd_rn((double)k, 0.5), 0x1p-52);
 }
-__device__ __forceinline__ double marginal(int kind, double a, double b, double u) {
+// ---------------------------------------------------------------- inverse CDFs of the marginals (bk_marginal_kind)
+// log Beta(a, b) prefactor and continued fraction of the regularised incomplete beta function (modified Lentz,
+// DLMF 8.17.22); converges in O(sqrt(max(a, b))) terms for x < (a + 1) / (a + b + 2).
+static __device__ __noinline__ double beta_cf(double a, double b, double x) {
+    const double tiny = 1e-300, qab = a + b, qap = a + 1.0, qam = a - 1.0;
+    double c = 1.0, d = 1.0 - qab * x / qap;
+    if (fabs(d) < tiny) d = tiny;
+    d = 1.0 / d;
+    double h = d;
+    for (int m = 1; m <= 600; ++m) {
+        const double m2 = 2.0 * m;
+        double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+        d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        h *= d * c;
+        aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+        d = 1.0 + aa * d; if (fabs(d) < tiny) d = tiny;
+        c = 1.0 + aa / c; if (fabs(c) < tiny) c = tiny;
+        d = 1.0 / d;
+        const double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < 1e-16) break;
+    }
+    return h;
+}
+static __device__ __noinline__ double beta_inc(double a, double b, double x, double lbeta) {   // I_x(a, b)
+    if (x <= 0.0) return 0.0;
+    if (x >= 1.0) return 1.0;
+    const double bt = exp(a * log(x) + b * log1p(-x) - lbeta);
+    if (x < (a + 1.0) / (a + b + 2.0)) return bt * beta_cf(a, b, x) / a;
+    return 1.0 - bt * beta_cf(b, a, 1.0 - x) / b;
+}
+// x with I_x(a, b) = u: AS 109 starting value, then safeguarded Halley steps on I_x - u (cubic convergence; the
+// bracket [lo, hi] keeps every iterate inside (0, 1))
+static __device__ __noinline__ double beta_inc_inv(double a, double b, double u) {
+    const double lbeta = lgamma(a) + lgamma(b) - lgamma(a + b);
+    double x;
+    if (a >= 1.0 && b >= 1.0) {
+        const double pp = u < 0.5 ? u : 1.0 - u;
+        const double t = sqrt(-2.0 * log(pp));
+        double z = (2.30753 + t * 0.27061) / (1.0 + t * (0.99229 + t * 0.04481)) - t;
+        if (u < 0.5) z = -z;
+        const double al = (z * z - 3.0) / 6.0;
+        const double h = 2.0 / (1.0 / (2.0 * a - 1.0) + 1.0 / (2.0 * b - 1.0));
+        const double w = z * sqrt(al + h) / h - (1.0 / (2.0 * b - 1.0) - 1.0 / (2.0 * a - 1.0)) * (al + 5.0 / 6.0 - 2.0 / (3.0 * h));
+        x = a / (a + b * exp(2.0 * w));
+    } else {
+        const double lna = log(a / (a + b)), lnb = log(b / (a + b));
+        const double t = exp(a * lna) / a, t1 = exp(b * lnb) / b, w = t + t1;
+        x = u < t / w ? pow(a * w * u, 1.0 / a) : 1.0 - pow(b * w * (1.0 - u), 1.0 / b);
+    }
+    double lo = 0.0, hi = 1.0;
+    if (!(x > 0.0 && x < 1.0)) x = 0.5;
+    for (int it = 0; it < 60; ++it) {
+        const double err = beta_inc(a, b, x, lbeta) - u;
+        if (err > 0.0) hi = x; else lo = x;
+        const double pdf = exp((a - 1.0) * log(x) + (b - 1.0) * log1p(-x) - lbeta);
+        double xn;
+        if (pdf > 0.0 && isfinite(pdf)) {
+            const double st = err / pdf;
+            double corr = 0.5 * st * ((a - 1.0) / x - (b - 1.0) / (1.0 - x));
+            if (corr > 0.5) corr = 0.5;
+            if (corr < -0.5) corr = -0.5;
+            xn = x - st / (1.0 - corr);
+        } else {
+            xn = 0.5 * (lo + hi);
+        }
+        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);              // left the bracket: bisect
+        const double dx = fabs(xn - x);
+        x = xn;
+        if (dx <= 4e-16 * x || hi - lo <= 4e-16 * x) break;
+    }
+    return x;
+}
+
+// par = the BK_MARGINAL_NPAR parameters of the marginal (include/batman_b200.h)
+__device__ __forceinline__ double marginal(int kind, double a, double b, double c, double d, double u) {
     if (kind == BK_UNIFORM) return __dadd_rn(a, __dmul_rn(__dadd_rn(b, -a), u));   // a + (b - a) * u
-    return __dadd_rn(a, __dmul_rn(b, normcdfinv(u)));                              // mu + sigma * ndtri(u)
+    if (kind == BK_NORMAL) return __dadd_rn(a, __dmul_rn(b, normcdfinv(u)));       // mu + sigma * ndtri(u)
+    switch (kind) {
+        case BK_LOGNORMAL: return c + exp(a + b * normcdfinv(u));
+        case BK_TRIANGULAR: {
+            const double fm = (b - a) / (c - a);
+            return u < fm ? a + sqrt(u * (c - a) * (b - a)) : c - sqrt((1.0 - u) * (c - a) * (c - b));
+        }
+        case BK_TRUNCNORMAL: return a + b * normcdfinv(c + u * (d - c));
+        case BK_BETA: return c + (d - c) * beta_inc_inv(a, b, u);
+        case BK_GUMBEL: return b - a * log(-log(u));
+        case BK_EXPONENTIAL: return b - log1p(-u) / a;
+        case BK_LOGUNIFORM: return exp(a + (b - a) * u);
+        case BK_WEIBULLMIN: return c + a * pow(-log1p(-u), 1.0 / b);
+        case BK_LOGISTIC: return a + b * (log(u) - log1p(-u));
+        case BK_RAYLEIGH: return b + a * sqrt(-2.0 * log1p(-u));
+    }
+    return u;
+}
+// marginal parameters as the kernels carry them: par[k][column]
+template <int P>
+struct MargPar {
+    int kind[P];
+    double par[BK_MARGINAL_NPAR][P];
+};
+template <int P>
+__host__ inline void marg_fill(MargPar<P>& mp, int p, const int* mkind, const double* mpar) {
+    for (int c = 0; c < P; ++c) {
+        mp.kind[c] = (c < p && mkind) ? mkind[c] : 0;
+        for (int k = 0; k < BK_MARGINAL_NPAR; ++k) mp.par[k][c] = (c < p && mpar) ? mpar[BK_MARGINAL_NPAR * c + k] : 0.0;
+    }
 }
 template <int P>
-__device__ __forceinline__ void design_row(uint64_t seed, uint64_t row, int p, int stream, const int* kind,
-                                           const double* pa, const double* pb, double x[P]) {
+__device__ __forceinline__ double marginal_col(const MargPar<P>& mp, int c, double u) {
+    return marginal(mp.kind[c], mp.par[0][c], mp.par[1][c], mp.par[2][c], mp.par[3][c], u);
+}
+template <int P>
+__device__ __forceinline__ void design_row(uint64_t seed, uint64_t row, int p, int stream, const MargPar<P>& mp,
+                                           double x[P]) {
 #pragma unroll
     for (int cp = 0; cp < P / 2; ++cp) {
         if (2 * cp < p) {
             uint32_t w[4];
             philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), (uint32_t)cp, (uint32_t)stream, (uint32_t)seed,
                           (uint32_t)(seed >> 32), w);
-            x[2 * cp] = marginal(kind[2 * cp], pa[2 * cp], pb[2 * cp], unit_from_words(w[0], w[1]));
-            x[2 * cp + 1] = (2 * cp + 1 < p)
-                                ? marginal(kind[2 * cp + 1], pa[2 * cp + 1], pb[2 * cp + 1], unit_from_words(w[2], w[3]))
-                                : 0.0;
+            x[2 * cp] = marginal_col<P>(mp, 2 * cp, unit_from_words(w[0], w[1]));
+            x[2 * cp + 1] = (2 * cp + 1 < p) ? marginal_col<P>(mp, 2 * cp + 1, unit_from_words(w[2], w[3])) : 0.0;
         } else {
             x[2 * cp] = 0.0;
             x[2 * cp + 1] = 0.0;
@@ -142,8 +250,7 @@ struct SobolParams {
     const double* a;       // count x p explicit base samples, or null -> Philox
     const double* b;
     uint64_t seed;
-    int mkind[P];
-    double mpa[P], mpb[P];
+    MargPar<P> marg;
     long row_lo, count;
     int p, second, nb, nsums;
     int n_pad;

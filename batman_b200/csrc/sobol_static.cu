@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(SOB_THREADS) k_sobol_static(const SobolParams<
                     xb[c] = c < prm.p ? prm.b[gc * prm.p + c] : 0.0;
                 }
             } else {
-                design_row<P>(prm.seed, (uint64_t)(prm.row_lo + gc), prm.p, 0, prm.mkind, prm.mpa, prm.mpb, xa);
-                design_row<P>(prm.seed, (uint64_t)(prm.row_lo + gc), prm.p, 1, prm.mkind, prm.mpa, prm.mpb, xb);
+                design_row<P>(prm.seed, (uint64_t)(prm.row_lo + gc), prm.p, 0, prm.marg, xa);
+                design_row<P>(prm.seed, (uint64_t)(prm.row_lo + gc), prm.p, 1, prm.marg, xb);
             }
 #pragma unroll
             for (int c = 0; c < P; ++c) {

@@ -38,7 +38,24 @@ enum bk_kind {
     BK_GENERAL = 5     /* expanded Sum/Product tree with several stationary leaves (bk_gp_set_output_general) */
 };
 
-enum bk_marginal_kind { BK_UNIFORM = 0, BK_NORMAL = 1 };
+/* Marginals of the UQ inputs: ot.<Name>(...) strings of uq.py:151-155, OpenTURNS 1.15 parametrisations.  Every marginal
+ * carries BK_MARGINAL_NPAR = 4 doubles (unused ones 0); a sample is the inverse CDF of a Philox uniform in (0, 1). */
+enum bk_marginal_kind {
+    BK_UNIFORM = 0,      /* (a, b)                      a + (b - a) u */
+    BK_NORMAL = 1,       /* (mu, sigma)                 mu + sigma ndtri(u) */
+    BK_LOGNORMAL = 2,    /* (muLog, sigmaLog, gamma)    gamma + exp(muLog + sigmaLog ndtri(u)) */
+    BK_TRIANGULAR = 3,   /* (a, m, b) */
+    BK_TRUNCNORMAL = 4,  /* (mu, sigma, Phi((a-mu)/sigma), Phi((b-mu)/sigma)): the host evaluates the two CDF values */
+    BK_BETA = 5,         /* (alpha, beta, a, b)         a + (b - a) betaincinv(alpha, beta, u); also BetaMuSigma */
+    BK_GUMBEL = 6,       /* (beta, gamma)               gamma - beta log(-log u) */
+    BK_EXPONENTIAL = 7,  /* (lambda, gamma)             gamma - log(1 - u) / lambda */
+    BK_LOGUNIFORM = 8,   /* (aLog, bLog)                exp(aLog + (bLog - aLog) u) */
+    BK_WEIBULLMIN = 9,   /* (beta, alpha, gamma)        gamma + beta (-log(1 - u))^(1/alpha) */
+    BK_LOGISTIC = 10,    /* (mu, beta)                  mu + beta log(u / (1 - u)) */
+    BK_RAYLEIGH = 11,    /* (beta, gamma)               gamma + beta sqrt(-2 log(1 - u)) */
+    BK_MARGINAL_COUNT = 12
+};
+#define BK_MARGINAL_NPAR 4
 
 int bk_version(void);
 const char* bk_last_error(void);

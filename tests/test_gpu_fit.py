@@ -123,7 +123,11 @@ def test_c_abi_lml_and_sobol_stay_inside_their_buffers():
     X, y = _data(n, p)
     yn, _, _ = normalise_y(y)
     # the C ABI takes dense row-major buffers (scipy's Halton points are Fortran-ordered)
-    Xd, yd = torch.from_numpy(np.ascontiguousarray(X)).cuda(), torch.from_numpy(np.ascontiguousarray(yn)).cuda()
+    y2 = np.cos(3.0 * X).sum(axis=1)                      # a second output: candidates of several outputs share a call
+    yn2, _, _ = normalise_y(y2)
+    Xd = torch.from_numpy(np.ascontiguousarray(X)).cuda()
+    yd = torch.from_numpy(np.ascontiguousarray(np.stack([yn, yn2]))).cuda()
+    targets = [0, 1, 0, 1, 1]
     kern = ConstantKernel(1.3) * Matern(length_scale=[0.8] * p, nu=1.5)
     rng = np.random.RandomState(0)
     specs = [kernel_spec.flatten(kern.clone_with_theta(kern.theta + rng.uniform(-0.5, 0.5, p + 1)), p) for _ in range(R)]
@@ -132,15 +136,15 @@ def test_c_abi_lml_and_sobol_stay_inside_their_buffers():
     ws = torch.full((need // 8 + 1 + pad,), CAN, dtype=torch.float64, device='cuda')
     lml = torch.full((R + 64,), CAN, dtype=torch.float64, device='cuda')
     vp = lambda t: ctypes.c_void_p(t.data_ptr())
-    _lib.check(lib.bk_lml_batched(vp(Xd), vp(yd), n, p, R, _lib.as_int_array([s.kind for s in specs]),
+    _lib.check(lib.bk_lml_batched(vp(Xd), vp(yd), 2, _lib.as_int_array(targets), n, p, R,
+                                  _lib.as_int_array([s.kind for s in specs]),
                                   _lib.as_double_array([s.c0 for s in specs]), _lib.as_double_array([s.c1 for s in specs]),
                                   _lib.as_double_array([s.kdiag for s in specs]),
                                   _lib.as_double_array(np.concatenate([s.ls for s in specs])), vp(lml), vp(ws), need, None))
     torch.cuda.synchronize()
     assert bool((ws[need // 8 + 1:] == CAN).all()) and bool((lml[R:] == CAN).all())
-    gp = GaussianProcessRegressor(kernel=kern, normalize_y=True, optimizer=None).fit(X, y)
-    want = [gp.log_marginal_likelihood(kern.theta + d) for d in
-            [np.log(np.r_[s.c1, s.ls]) - kern.theta for s in specs]]
+    gps = [GaussianProcessRegressor(kernel=kern, normalize_y=True, optimizer=None).fit(X, yy) for yy in (y, y2)]
+    want = [gps[t].log_marginal_likelihood(np.log(np.r_[s.c1, s.ls])) for s, t in zip(specs, targets)]
     np.testing.assert_allclose(lml[:R].cpu().numpy(), want, rtol=1e-9, atol=1e-7)
 
 

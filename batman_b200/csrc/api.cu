@@ -81,6 +81,11 @@ int gp_factorise_general(const double* X, const double* y, int n, int p, int nf,
                          double* lml_out, int* info_out, void* ws, size_t ws_bytes, cudaStream_t st);
 int tri_inverse_pack(const double* L, int n, double* wt_tiles_out, int8_t* wq_out, double* wsig_out, int wq_scheme,
                      void* ws, size_t ws_bytes, cudaStream_t st);
+int launch_lhs_rows(uint64_t seed, long count, int p, const int* mkind, const double* mpar, const long* perm,
+                    double* out, cudaStream_t st);
+int launch_moments(const double* y, long rows, int F, const double* shift, double* out, cudaStream_t st);
+int launch_sobol_asym(const double* z, long ld_block, long count, int p, int r, const double* center, double* sums,
+                      cudaStream_t st);
 int sobol_nsums_host(int p, int second);
 int sobol_nslots_host();
 
@@ -89,6 +94,12 @@ constexpr long PRED_CHUNK_ALIGN = 256;   // k_predict covers 2 tiles of 128 poin
 }  // namespace bk
 
 using namespace bk;
+
+static int check_marginals(const char* who, int p, const int* kind) {
+    for (int c = 0; c < p; ++c)
+        if (kind[c] < 0 || kind[c] >= BK_MARGINAL_COUNT) return set_error("%s: marginal %d has unknown kind %d", who, c, kind[c]);
+    return 0;
+}
 
 extern "C" {
 
@@ -380,12 +391,6 @@ int bk_tri_inverse_pack(const double* l_dev, int n_train, double* w_tiles_dev, i
                             (cudaStream_t)stream);
 }
 
-static int check_marginals(const char* who, int p, const int* kind) {
-    for (int c = 0; c < p; ++c)
-        if (kind[c] < 0 || kind[c] >= BK_MARGINAL_COUNT) return set_error("%s: marginal %d has unknown kind %d", who, c, kind[c]);
-    return 0;
-}
-
 int bk_sobol_nsums(int p, int second_order) { return sobol_nsums_host(p, second_order); }
 int bk_sobol_nslots(void) { return sobol_nslots_host(); }
 
@@ -413,6 +418,46 @@ int bk_sobol_accumulate(bk_gp_t h, const double* a_dev, const double* b_dev, uin
                                   (cudaStream_t)stream))
             return rc;
     return 0;
+}
+
+int bk_sobol_accumulate_keep(bk_gp_t h, const double* a_dev, const double* b_dev, uint64_t seed,
+                             const int* marg_kind_host, const double* marg_par_host, long row_lo, long count,
+                             int second_order, const double* shift_host, double* partials_dev, double* ykeep_dev,
+                             void* stream) {
+    if (!h || !partials_dev || !ykeep_dev) return set_error("bk_sobol_accumulate_keep: NULL pointer");
+    if ((a_dev == nullptr) != (b_dev == nullptr)) return set_error("bk_sobol_accumulate_keep: a_dev and b_dev must both be given or both NULL");
+    if (!a_dev && (!marg_kind_host || !marg_par_host))
+        return set_error("bk_sobol_accumulate_keep: no base samples and no marginals to generate them from");
+    if (!a_dev)
+        if (int rc = check_marginals("bk_sobol_accumulate_keep", h->p, marg_kind_host)) return rc;
+    if (count <= 0) return 0;
+    for (int q = 0; q < h->m; ++q)
+        if (int rc = launch_sobol(h, q, a_dev, b_dev, seed, marg_kind_host, marg_par_host, row_lo, count,
+                                  second_order ? 1 : 0, shift_host ? shift_host[q] : 0.0, partials_dev, ykeep_dev,
+                                  (cudaStream_t)stream))
+            return rc;
+    return 0;
+}
+
+int bk_sobol_asymptotic(const double* z_dev, long ld_block, long count, int p, int r, const double* center_dev,
+                        double* sums_dev, void* stream) {
+    if (!z_dev || !center_dev || !sums_dev) return set_error("bk_sobol_asymptotic: NULL pointer");
+    if (p < 1 || r < 1 || ld_block < count) return set_error("bk_sobol_asymptotic: need p >= 1, r >= 1, ld_block >= count");
+    return launch_sobol_asym(z_dev, ld_block, count, p, r, center_dev, sums_dev, (cudaStream_t)stream);
+}
+
+int bk_lhs_rows(uint64_t seed, long count, int p, const int* marg_kind_host, const double* marg_par_host,
+                const long* perm_dev, double* out_dev, void* stream) {
+    if (!marg_kind_host || !marg_par_host || !perm_dev || !out_dev) return set_error("bk_lhs_rows: NULL pointer");
+    if (p < 1) return set_error("bk_lhs_rows: p must be >= 1");
+    if (int rc = check_marginals("bk_lhs_rows", p, marg_kind_host)) return rc;
+    return launch_lhs_rows(seed, count, p, marg_kind_host, marg_par_host, perm_dev, out_dev, (cudaStream_t)stream);
+}
+
+int bk_moments(const double* y_dev, long rows, int F, const double* shift_dev, double* out_dev, void* stream) {
+    if (!y_dev || !out_dev) return set_error("bk_moments: NULL pointer");
+    if (F < 1) return set_error("bk_moments: F must be >= 1");
+    return launch_moments(y_dev, rows, F, shift_dev, out_dev, (cudaStream_t)stream);
 }
 
 int bk_sobol_modes(bk_gp_t h, const double* a_dev, const double* b_dev, uint64_t seed, const int* marg_kind_host,

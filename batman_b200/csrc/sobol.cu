@@ -134,20 +134,17 @@ __global__ void __launch_bounds__(SOB_THREADS) k_sobol(const SobolParams<P> prm)
             for (int bb = 0; bb < SOB_CH; ++bb) {
                 if (b0 + bb < prm.nb) {
                     const double y = __dadd_rn(__dmul_rn(prm.y_std, acc[bb]), prm.y_mean);
-                    if (prm.yout) {
-                        if (valid) prm.yout[((size_t)(b0 + bb) * prm.count + g) * prm.m + prm.q] = y;
-                    } else {
-                        y_s[(b0 + bb) * SOB_THREADS + tid] = valid ? __dadd_rn(y, -prm.shift) : 0.0;
-                    }
+                    if (prm.yout && valid) prm.yout[((size_t)(b0 + bb) * prm.count + g) * prm.m + prm.q] = y;
+                    if (prm.partial) y_s[(b0 + bb) * SOB_THREADS + tid] = valid ? __dadd_rn(y, -prm.shift) : 0.0;
                 }
             }
         }
-        if (!prm.yout)
+        if (prm.partial)
             saltelli_products([&](int b) { return y_s[b * SOB_THREADS + tid]; }, prm.p, prm.second, lane,
                               wsum + (size_t)warp * prm.nsums * 2, valid ? 1.0 : 0.0);
     }
     __syncthreads();
-    if (!prm.yout)
+    if (prm.partial)
         flush_slot(wsum, SOB_THREADS / 32, prm.nsums, prm.partial + (size_t)blockIdx.x * prm.slot_stride);
 }
 
@@ -359,7 +356,7 @@ static int launch_sobol_general(const bk_gp_s* h, int q, const double* a, const 
         }
     } sc{st};
     BK_CUDA(cudaMallocAsync(&sc.design, sizeof(double) * slab_max * p, st));
-    if (!yout) {
+    if (partials) {
         BK_CUDA(cudaMallocAsync(&sc.ybuf, sizeof(double) * slab_max * nb, st));
         BK_CUDA(cudaMallocAsync(&sc.shift_dev, sizeof(double), st));
         BK_CUDA(cudaMemcpyAsync(sc.shift_dev, &shift, sizeof(double), cudaMemcpyHostToDevice, st));
@@ -381,13 +378,18 @@ static int launch_sobol_general(const bk_gp_s* h, int q, const double* a, const 
             bp.block = blk;
             k_design_block<<<(unsigned)((cnt + 127) / 128), 128, 0, st>>>(bp);
             if (cudaGetLastError() != cudaSuccess) { rc = set_error("k_design_block launch failed"); break; }
-            if (yout)     // yout[(blk * count + lo + k) * m + q]
+            if (!partials) {     // yout[(blk * count + lo + k) * m + q]
                 rc = launch_predict_general(h, q, design, cnt, yout + ((size_t)blk * count + lo) * h->m, h->m, q, nullptr,
                                             nullptr, 0, 1.0, st);
-            else          // ybuf[blk * cnt + k]
+            } else {             // ybuf[blk * cnt + k] (+ a strided copy when the caller keeps the outputs as well)
                 rc = launch_predict_general(h, q, design, cnt, ybuf + (size_t)blk * cnt, 1, 0, nullptr, nullptr, 0, 1.0, st);
+                if (rc == 0 && yout)
+                    BK_CUDA(cudaMemcpy2DAsync(yout + ((size_t)blk * count + lo) * h->m + q, sizeof(double) * h->m,
+                                              ybuf + (size_t)blk * cnt, sizeof(double), sizeof(double), cnt,
+                                              cudaMemcpyDeviceToDevice, st));
+            }
         }
-        if (rc == 0 && !yout)
+        if (rc == 0 && partials)
             rc = launch_sobol_y_ex(ybuf, cnt, cnt, p, 1, second, shift_dev, partials + (size_t)q * nsums * 2,
                                    (long)h->m * nsums * 2, st);
     }
@@ -416,7 +418,10 @@ int launch_reduce_slots(const double* partials, int F, int nsums, double* totals
 // uq/uq.py:400-436 for the aggregation).  With y' = y - shift the centred output is y' - delta, delta = mean
 // over ALL R rows of y'; every centred product follows algebraically, evaluated in double-double.
 struct FinalizeLayout {
-    size_t S1, ST, S2, V1, VT, var, outvar, J1, JT, S1agg, STagg, S2agg, total;
+    size_t S1, ST, S2, V1, VT, var, outvar, J1, JT, S1agg, STagg, S2agg;
+    size_t M1, MT, K1, KT;                                  // Martinez, Mauntz-Kucherenko (per feature)
+    size_t J1agg, JTagg, M1agg, MTagg, K1agg, KTagg, mean;  // aggregated variants; mean of every output over all rows
+    size_t total;
 };
 __host__ __device__ inline FinalizeLayout finalize_layout(int p, int F) {
     FinalizeLayout L;
@@ -433,6 +438,17 @@ __host__ __device__ inline FinalizeLayout finalize_layout(int p, int F) {
     L.S1agg = o; o += p;
     L.STagg = o; o += p;
     L.S2agg = o; o += (size_t)p * p;
+    L.M1 = o; o += (size_t)F * p;
+    L.MT = o; o += (size_t)F * p;
+    L.K1 = o; o += (size_t)F * p;
+    L.KT = o; o += (size_t)F * p;
+    L.J1agg = o; o += p;
+    L.JTagg = o; o += p;
+    L.M1agg = o; o += p;
+    L.MTagg = o; o += p;
+    L.K1agg = o; o += p;
+    L.KTagg = o; o += p;
+    L.mean = o; o += F;
     L.total = o;
     return L;
 }
@@ -463,7 +479,14 @@ __global__ void k_finalize_feature(const double* __restrict__ totals, long N, in
     const dd outvar = dd_div(dd_sub(sq_all, dd_mul(dR, dd_mul(delta, delta))), dR); // output_design.var(axis=0)
     out[L.var + f] = dd_to_double(var);
     out[L.outvar + f] = dd_to_double(outvar);
+    out[L.mean + f] = dd_to_double(delta);                 // mean over all rows of y - shift (the host adds the shift)
     const dd d2N1 = dd_from((double)(2 * N - 1));
+    // other estimators from the same sums (the comment of uq.py:340 names them; conventions: oracle/saltelli.py).
+    // Martinez: S_i = corr(yB, yE^i), ST_i = 1 - corr(yA, yE^i) (shift invariant: no centring needed);
+    // Mauntz-Kucherenko: V_i = sum yB (yE^i - yA) / (N - 1), VT_i = sum yA (yA - yE^i) / (N - 1) on the centred output.
+    const dd ssA = dd_sub(S(2), dd_div(dd_mul(SA, SA), dN));                         // sum (yA - mean yA)^2
+    const dd ssB = dd_sub(S(3), dd_div(dd_mul(SB, SB), dN));
+    const dd cAA = cdot(S(2), SA, SA), cAB = cdot(S(4), SA, SB);
     for (int i = 0; i < p; ++i) {
         const int b = 5 + 6 * i;
         const dd SE = S(b);
@@ -475,6 +498,14 @@ __global__ void k_finalize_feature(const double* __restrict__ totals, long N, in
         out[L.ST + (size_t)f * p + i] = dd_to_double(dd_div(VT, var));
         out[L.J1 + (size_t)f * p + i] = dd_to_double(dd_div(dd_sub(var, dd_div(S(b + 4), d2N1)), var));
         out[L.JT + (size_t)f * p + i] = dd_to_double(dd_div(dd_div(S(b + 5), d2N1), var));
+        const dd ssE = dd_sub(S(b + 1), dd_div(dd_mul(SE, SE), dN));
+        const double covBE = dd_to_double(dd_sub(S(b + 2), dd_div(dd_mul(SB, SE), dN)));
+        const double covAE = dd_to_double(dd_sub(S(b + 3), dd_div(dd_mul(SA, SE), dN)));
+        out[L.M1 + (size_t)f * p + i] = covBE / sqrt(dd_to_double(ssB) * dd_to_double(ssE));
+        out[L.MT + (size_t)f * p + i] = 1.0 - covAE / sqrt(dd_to_double(ssA) * dd_to_double(ssE));
+        const dd cBE = cdot(S(b + 2), SB, SE), cAE = cdot(S(b + 3), SA, SE);
+        out[L.K1 + (size_t)f * p + i] = dd_to_double(dd_div(dd_div(dd_sub(cBE, cAB), dN1), var));
+        out[L.KT + (size_t)f * p + i] = dd_to_double(dd_div(dd_div(dd_sub(cAA, cAE), dN1), var));
     }
     for (int i = 0; i < p; ++i)
         for (int j = 0; j < p; ++j) out[L.S2 + ((size_t)f * p + i) * p + j] = 0.0;
@@ -508,6 +539,18 @@ __global__ void k_finalize_aggregate(int p, int F, double* __restrict__ out) {
         }
         out[L.S1agg + t] = dd_to_double(dd_div(s1, sv));
         out[L.STagg + t] = dd_to_double(dd_div(st, sv));
+        // every estimator aggregates the same way: sum_q (index_q * Var_q) / sum_q Var_q
+        const size_t src[6] = {L.J1, L.JT, L.M1, L.MT, L.K1, L.KT};
+        const size_t dst[6] = {L.J1agg, L.JTagg, L.M1agg, L.MTagg, L.K1agg, L.KTagg};
+        for (int e = 0; e < 6; ++e) {
+            dd acc{0, 0};
+            for (int f = 0; f < F; ++f) {
+                double p_, e_;
+                two_prod(out[src[e] + (size_t)f * p + t], out[L.var + f], p_, e_);
+                acc = dd_add(acc, dd{p_, e_});
+            }
+            out[dst[e] + t] = dd_to_double(dd_div(acc, sv));
+        }
     }
     for (int e = t; e < p * p; e += blockDim.x) {
         dd so{0, 0}, s2{0, 0};

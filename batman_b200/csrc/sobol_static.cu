@@ -99,11 +99,8 @@ __device__ __forceinline__ void ss_pass(StaticCtx<P>& cx, const double (&ua)[P],
         if (i < prm.p) {                                     // drop blocks of padded dimensions
             const int b = lb < 2 + P ? (lb < 2 ? lb : 2 + i) : 2 + prm.p + i;
             const double y = __dadd_rn(__dmul_rn(prm.y_std, acc[bb]), prm.y_mean);
-            if (prm.yout) {
-                if (cx.valid) prm.yout[((size_t)b * prm.count + cx.g) * prm.m + prm.q] = y;
-            } else {
-                cx.y_s[b * SOB_THREADS + cx.tid] = cx.valid ? __dadd_rn(y, -prm.shift) : 0.0;
-            }
+            if (prm.yout && cx.valid) prm.yout[((size_t)b * prm.count + cx.g) * prm.m + prm.q] = y;
+            if (prm.partial) cx.y_s[b * SOB_THREADS + cx.tid] = cx.valid ? __dadd_rn(y, -prm.shift) : 0.0;
         }
     }
 }
@@ -172,12 +169,12 @@ __global__ void __launch_bounds__(SOB_THREADS) k_sobol_static(const SobolParams<
             }
         }
         ss_passes<KIND, P, NLB, 0>(cx, ua, ub);
-        if (!prm.yout)
+        if (prm.partial)
             saltelli_products([&](int b) { return y_s[b * SOB_THREADS + tid]; }, prm.p, prm.second, lane,
                               wsum + (size_t)warp * prm.nsums * 2, cx.valid ? 1.0 : 0.0);
     }
     __syncthreads();
-    if (!prm.yout)
+    if (prm.partial)
         flush_slot(wsum, SOB_THREADS / 32, prm.nsums, prm.partial + (size_t)blockIdx.x * prm.slot_stride);
 }
 

@@ -531,7 +531,7 @@ def main():
     model = surrogate.predictor._model()
     model.ensure_w()
     kinds = _lib.as_int_array([0] * P_DIM)
-    params = _lib.as_double_array([0.0, 1.0] * P_DIM)
+    params = _lib.as_double_array([0.0, 1.0, 0.0, 0.0] * P_DIM)        # Uniform(0, 1): 4 parameters per marginal
     row_lo = rank * args.n_base
     A = torch.empty((args.n_base, P_DIM), dtype=torch.float64, device=dev)
     B = torch.empty_like(A)

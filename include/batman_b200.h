@@ -214,11 +214,36 @@ int bk_sobol_reduce_slots(const double* partials_dev, int F, int nsums, double* 
  * {active (1/0), rows in the group, S1agg without the group [p], STagg without the group [p]}. */
 int bk_sobol_jackknife(const double* partials_dev, const double* totals_dev, long N, int p, int F, int second_order,
                        double* out_dev, void* stream);
+/* Asymptotic (delta-method) intervals, the method OpenTURNS itself uses for uq.py:341, 425-426: from the STORED outputs of
+ * the A, B and E^i blocks (z_dev[(b * ld_block + k) * r + c], b = 0: A, 1: B, 2+i: E^i; r outputs per row; what
+ * bk_sobol_modes / bk_sobol_accumulate_keep wrote) and the per-output mean over all rows of the experiment (center_dev,
+ * r values, known after bk_sobol_finalize), ADD into sums_dev ((2 + 6p) x 2 doubles (hi, lo), zero before the first
+ * chunk) the sums over base rows of  b, b^2, and per input i: a1, a1^2, a1 b, a2, a2^2, a2 b  with
+ * b = <zA, zA>, a1 = <zB, zE^i>, a2 = <zA, zE^i> (dot products over the r centred outputs).  The host forms
+ * Var(S_i) = grad(psi)^T Cov(a1, b) grad(psi) / N for psi(x, y) = x / y (total order: 1 - x / y). */
+int bk_sobol_asymptotic(const double* z_dev, long ld_block, long count, int p, int r, const double* center_dev,
+                        double* sums_dev, void* stream);
+/* bk_sobol_accumulate that ALSO keeps the outputs: ykeep_dev[(b * count + k) * m + q] for every block b (the layout of
+ * bk_sobol_modes), so that the interval pass does not predict again. */
+int bk_sobol_accumulate_keep(bk_gp_t h, const double* a_dev, const double* b_dev, uint64_t seed,
+                             const int* marg_kind_host, const double* marg_par_host, long row_lo, long count,
+                             int second_order, const double* shift_host, double* partials_dev, double* ykeep_dev,
+                             void* stream);
+/* The N-point randomised LHS of UQ.__init__ (ot.LHSExperiment(dist, N, True, True), uq.py:159-160): row i, column c is
+ * the inverse CDF of (perm_dev[i * p + c] + shift) / count, shift = the Philox uniform of (row i, column c, stream 2);
+ * perm_dev (count x p int64): every column a permutation of 0 .. count-1.  out_dev count x p. */
+int bk_lhs_rows(uint64_t seed, long count, int p, const int* marg_kind_host, const double* marg_par_host,
+                const long* perm_dev, double* out_dev, void* stream);
+/* Moments of a stored output sample y_dev (rows x F row-major), what UQ.error_propagation reports (uq.py:501-529):
+ * out_dev F x 6 = {sum hi, sum lo, sum of squares hi, lo (both of y - shift_dev[f]; shift_dev may be NULL), min, max}. */
+int bk_moments(const double* y_dev, long rows, int F, const double* shift_dev, double* out_dev, void* stream);
 /* doubles in the packed result of bk_sobol_finalize */
 size_t bk_sobol_result_len(int p, int F);
 /* Estimators from the totals.  out_dev layout (row-major, all double):
  *   S1[F][p] ST[F][p] S2[F][p][p] V1[F][p] VT[F][p] var[F] outvar[F] J1[F][p] JT[F][p]
- *   S1agg[p] STagg[p] S2agg[p][p] */
+ *   S1agg[p] STagg[p] S2agg[p][p]
+ *   M1[F][p] MT[F][p] (Martinez) K1[F][p] KT[F][p] (Mauntz-Kucherenko) -- the other OpenTURNS estimators uq.py:340 names
+ *   J1agg[p] JTagg[p] M1agg[p] MTagg[p] K1agg[p] KTagg[p]  mean[F] (of y - shift over all rows) */
 int bk_sobol_finalize(const double* totals_dev, long N, int p, int F, int second_order,
                       double* out_dev, void* stream);
 

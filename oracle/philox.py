@@ -65,17 +65,45 @@ def uniforms(seed, rows, p, stream):
 
 
 def marginal_transform(u, dists):
-    """dists: list of ('uniform', a, b) | ('normal', mu, sigma), one per column."""
-    from scipy.special import ndtri
+    """dists: one tuple per column, ('uniform', a, b) | ('normal', mu, sigma) | ('lognormal', muLog, sigmaLog, gamma) |
+    ('triangular', a, m, b) | ('truncatednormal', mu, sigma, Phi_a, Phi_b) | ('beta', alpha, beta, a, b) |
+    ('gumbel', beta, gamma) | ('exponential', lambda, gamma) | ('loguniform', aLog, bLog) |
+    ('weibullmin', beta, alpha, gamma) | ('logistic', mu, beta) | ('rayleigh', beta, gamma): the inverse CDFs of
+    OpenTURNS 1.15's parametrisations on scipy.special (the device twins: csrc/sobol_common.cuh ``marginal``)."""
+    from scipy import special
     x = np.empty_like(u)
     for j, d in enumerate(dists):
-        if d[0] == 'uniform':
-            a, b = float(d[1]), float(d[2])
-            x[:, j] = a + (b - a) * u[:, j]
-        elif d[0] == 'normal':
-            x[:, j] = float(d[1]) + float(d[2]) * ndtri(u[:, j])
+        name = d[0]
+        par = [float(v) for v in d[1:]] + [0.0] * (5 - len(d))
+        a, b, c, e = par
+        uj = u[:, j]
+        if name == 'uniform':
+            x[:, j] = a + (b - a) * uj
+        elif name == 'normal':
+            x[:, j] = a + b * special.ndtri(uj)
+        elif name == 'lognormal':
+            x[:, j] = c + np.exp(a + b * special.ndtri(uj))
+        elif name == 'triangular':
+            fm = (b - a) / (c - a)
+            x[:, j] = np.where(uj < fm, a + np.sqrt(uj * (c - a) * (b - a)), c - np.sqrt((1.0 - uj) * (c - a) * (c - b)))
+        elif name == 'truncatednormal':
+            x[:, j] = a + b * special.ndtri(c + uj * (e - c))
+        elif name == 'beta':
+            x[:, j] = c + (e - c) * special.betaincinv(a, b, uj)
+        elif name == 'gumbel':
+            x[:, j] = b - a * np.log(-np.log(uj))
+        elif name == 'exponential':
+            x[:, j] = b - np.log1p(-uj) / a
+        elif name == 'loguniform':
+            x[:, j] = np.exp(a + (b - a) * uj)
+        elif name == 'weibullmin':
+            x[:, j] = c + a * np.power(-np.log1p(-uj), 1.0 / b)
+        elif name == 'logistic':
+            x[:, j] = a + b * (np.log(uj) - np.log1p(-uj))
+        elif name == 'rayleigh':
+            x[:, j] = b + a * np.sqrt(-2.0 * np.log1p(-uj))
         else:
-            raise NotImplementedError(d[0])
+            raise NotImplementedError(name)
     return x
 
 
@@ -86,3 +114,13 @@ def base_samples(seed, row_lo, row_hi, dists):
     A = marginal_transform(uniforms(seed, rows, p, 0), dists)
     B = marginal_transform(uniforms(seed, rows, p, 1), dists)
     return A, B
+
+
+def lhs_sample(seed, perm, dists):
+    """Randomised LHS (ot.LHSExperiment(dist, N, True, True), uq/uq.py:159-160) as the device draws it
+    (csrc/uq_extra.cu k_lhs_rows): cell perm[i, c] of row i in dimension c, in-cell shift = Philox stream 2,
+    u = (cell + shift) / N, then the marginal's inverse CDF.  perm: (N, p) integer array, every column a permutation."""
+    perm = np.asarray(perm)
+    n, p = perm.shape
+    shift = uniforms(seed, np.arange(n), p, 2)
+    return marginal_transform((perm.astype(np.float64) + shift) * (1.0 / n), dists)

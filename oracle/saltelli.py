@@ -126,6 +126,85 @@ def jansen_indices(Y, N, p):
     return {k: np.asarray(v, dtype=np.float64) for k, v in out.items()}
 
 
+def martinez_indices(Y, N, p):
+    """Martinez 2011 estimators on the same design (OT MartinezSensitivityAlgorithm; the reference's comment at
+    uq/uq.py:340 and doc/technical_documentation/uq.rst:64 name it):  S_i = corr(yB, yE^i),  ST_i = 1 - corr(yA, yE^i)
+    (Pearson correlations over the N base rows: invariant to the centring and to the variance normalisation).
+    Aggregation as for every OT estimator: sum_q S_i^q Var^q / sum_q Var^q.  PARITY UNPINNED (module header)."""
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.ndim == 1:
+        Y = Y[:, None]
+    Yl = Y.astype(LD)
+    yA, yB = Yl[0:N], Yl[N:2 * N]
+    var = yA.var(axis=0, ddof=1)
+    F = Y.shape[1]
+    S1 = np.zeros((F, p), dtype=LD)
+    ST = np.zeros((F, p), dtype=LD)
+    dA, dB = yA - yA.mean(axis=0), yB - yB.mean(axis=0)
+    for i in range(p):
+        yE = Yl[(2 + i) * N:(3 + i) * N]
+        dE = yE - yE.mean(axis=0)
+        S1[:, i] = (dB * dE).sum(axis=0) / np.sqrt((dB * dB).sum(axis=0) * (dE * dE).sum(axis=0))
+        ST[:, i] = 1 - (dA * dE).sum(axis=0) / np.sqrt((dA * dA).sum(axis=0) * (dE * dE).sum(axis=0))
+    out = dict(S1=S1, ST=ST, var=var, S1_agg=(S1 * var[:, None]).sum(axis=0) / var.sum(),
+               ST_agg=(ST * var[:, None]).sum(axis=0) / var.sum())
+    return {k: np.asarray(v, dtype=np.float64) for k, v in out.items()}
+
+
+def mauntz_kucherenko_indices(Y, N, p):
+    """Sobol'-Mauntz-Kucherenko 2007 estimators (OT MauntzKucherenkoSensitivityAlgorithm) on the centred output:
+    V_i = sum(yB (yE^i - yA)) / (N - 1),  VT_i = sum(yA (yA - yE^i)) / (N - 1).  PARITY UNPINNED (module header)."""
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.ndim == 1:
+        Y = Y[:, None]
+    Yc = Y.astype(LD) - Y.astype(LD).mean(axis=0)
+    yA, yB = Yc[0:N], Yc[N:2 * N]
+    var = yA.var(axis=0, ddof=1)
+    F = Y.shape[1]
+    V1 = np.zeros((F, p), dtype=LD)
+    VT = np.zeros((F, p), dtype=LD)
+    for i in range(p):
+        yE = Yc[(2 + i) * N:(3 + i) * N]
+        V1[:, i] = (yB * (yE - yA)).sum(axis=0) / (N - 1)
+        VT[:, i] = (yA * (yA - yE)).sum(axis=0) / (N - 1)
+    out = dict(S1=V1 / var[:, None], ST=VT / var[:, None], V1=V1, VT=VT, var=var,
+               S1_agg=V1.sum(axis=0) / var.sum(), ST_agg=VT.sum(axis=0) / var.sum())
+    return {k: np.asarray(v, dtype=np.float64) for k, v in out.items()}
+
+
+def asymptotic_sigma_aggregated(Y, N, p):
+    """Standard deviations of the asymptotic (delta-method) distribution of the aggregated Saltelli indices: what
+    ``ot.ResourceMap.SetAsBool('SobolIndicesAlgorithm-DefaultUseAsymptoticDistribution', True)`` selects for
+    ``getFirstOrderIndicesInterval()`` / ``getTotalOrderIndicesInterval()`` (uq/uq.py:341, 425-426).
+
+    Restated from the OpenTURNS 1.15 documentation of SaltelliSensitivityAlgorithm (PARITY UNPINNED, module header):
+    with the centred output, per base row k and aggregated over the outputs q,
+        first order  U_k = (sum_q yB_kq yE^i_kq, sum_q yA_kq^2),  psi(x, y) = x / y
+        total order  U_k = (sum_q yA_kq yE^i_kq, sum_q yA_kq^2),  psi(x, y) = 1 - x / y
+    and Var = grad psi(mean U)^T Cov(U) grad psi(mean U) / N with the unbiased sample covariance of U.
+    Returns (sigma_S1 (p,), sigma_ST (p,)); the 95 % interval is index -+ 1.959964 sigma."""
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.ndim == 1:
+        Y = Y[:, None]
+    Yc = Y.astype(LD) - Y.astype(LD).mean(axis=0)
+    yA, yB = Yc[0:N], Yc[N:2 * N]
+    b = (yA * yA).sum(axis=1)
+
+    def sigma(a):
+        x, y = a.mean(), b.mean()
+        cxx = ((a - x) ** 2).sum() / (N - 1)
+        cyy = ((b - y) ** 2).sum() / (N - 1)
+        cxy = ((a - x) * (b - y)).sum() / (N - 1)
+        return np.sqrt((cxx / y ** 2 - 2 * x * cxy / y ** 3 + x ** 2 * cyy / y ** 4) / N)
+    s1 = np.zeros(p, dtype=LD)
+    st = np.zeros(p, dtype=LD)
+    for i in range(p):
+        yE = Yc[(2 + i) * N:(3 + i) * N]
+        s1[i] = sigma((yB * yE).sum(axis=1))
+        st[i] = sigma((yA * yE).sum(axis=1))
+    return np.asarray(s1, dtype=np.float64), np.asarray(st, dtype=np.float64)
+
+
 def jackknife_aggregated(Y, N, p, groups, second_order=True):
     """Delete-a-group jackknife standard errors of the aggregated first / total order indices.
 

@@ -161,7 +161,7 @@ def test_c_abi_sobol_partials_canary():
     CAN, pad = -1.75, 4096
     part = torch.full((nslots * m * nsums * 2 + pad,), CAN, dtype=torch.float64, device='cuda')
     part[:nslots * m * nsums * 2] = 0.0
-    kinds, params = _lib.as_int_array([0] * p), _lib.as_double_array([0.0, 1.0] * p)
+    kinds, params = _lib.as_int_array([0] * p), _lib.as_double_array([0.0, 1.0, 0.0, 0.0] * p)
     _lib.check(lib.bk_sobol_accumulate(model.handle, None, None, 123456, kinds, params, 0, 12345, 1,
                                        _lib.as_double_array(model.y_means), ctypes.c_void_p(part.data_ptr()), None))
     torch.cuda.synchronize()

@@ -43,7 +43,7 @@ def test_device_generator_is_bit_exact_with_oracle_philox():
     dists = [('uniform', -3.0, 2.0), ('uniform', 0.0, 1.0), ('normal', 4035.0, 400.0), ('uniform', 15.0, 60.0),
              ('normal', 0.0, 1.0)]
     kinds = _lib.as_int_array([0 if d[0] == 'uniform' else 1 for d in dists])
-    params = _lib.as_double_array([v for d in dists for v in d[1:]])
+    params = _lib.as_double_array([v for d in dists for v in list(d[1:]) + [0.0, 0.0]])     # 4 parameters per marginal
     for stream in (0, 1):
         out = torch.empty((cnt, p), dtype=torch.float64, device='cuda')
         _lib.check(lib.bk_design_rows(seed, row_lo, cnt, p, kinds, params, stream, ctypes.c_void_p(out.data_ptr()), None))
@@ -172,7 +172,7 @@ def test_sobol_partials_are_additive_over_row_ranges():
     p, N = 3, 1000
     nsums, nslots = lib.bk_sobol_nsums(p, 1), lib.bk_sobol_nslots()
     kinds = _lib.as_int_array([0] * p)
-    params = _lib.as_double_array([-np.pi, np.pi] * p)
+    params = _lib.as_double_array([-np.pi, np.pi, 0.0, 0.0] * p)
     shift = _lib.as_double_array(model.y_means)
 
     def totals(ranges):
@@ -294,9 +294,10 @@ def test_sobol_intervals_jackknife_vs_oracle_and_files(tmp_path):
     dists = [('uniform', -np.pi, np.pi)] * 3
     A, B = philox.base_samples(123456, 0, N, dists)
     uq = UQ(s, dists=['Uniform(-3.141592653589793, 3.141592653589793)'] * 3, nsample=N, base_samples=(A, B),
-            fname=str(tmp_path), plabels=['x1', 'x2', 'x3'])
+            fname=str(tmp_path), plabels=['x1', 'x2', 'x3'], intervals='jackknife')
     s2, s1, st = uq.sobol()
     d = uq.details
+    assert d['interval_method'] == 'jackknife'
     assert d['jackknife_groups'] == (N + 127) // 128
     Y = _oracle_outputs(z, states, saltelli.design_from_base(A, B))
     theta, sigma = saltelli.jackknife_aggregated(Y, N, 3, (np.arange(N) // 128) % 592)

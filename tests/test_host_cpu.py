@@ -150,15 +150,52 @@ def test_kernel_flatten_rejects_unsupported():
 
 
 def test_distributions():
-    assert distributions.parse('Uniform(-3.1415, 3.1415)') == (0, -3.1415, 3.1415)
-    assert distributions.parse('Normal(4035., 400.)') == (1, 4035.0, 400.0)
-    assert distributions.parse(('uniform', 0, 1)) == (0, 0.0, 1.0)
+    assert distributions.parse('Uniform(-3.1415, 3.1415)') == (0, -3.1415, 3.1415, 0.0, 0.0)
+    assert distributions.parse('Normal(4035., 400.)') == (1, 4035.0, 400.0, 0.0, 0.0)
+    assert distributions.parse(('uniform', 0, 1)) == (0, 0.0, 1.0, 0.0, 0.0)
+    assert distributions.parse('Uniform()') == (0, -1.0, 1.0, 0.0, 0.0)              # OpenTURNS defaults
     with pytest.raises(SystemError):                 # uq.py:156-158
         distributions.parse('Unifrom(0, 1)')
-    with pytest.raises(NotImplementedError):
-        distributions.parse('BetaMuSigma(4035, 400, 2500, 6000).getDistribution()')
+    with pytest.raises(SystemError):                 # a parameter object without .getDistribution() is not a distribution
+        distributions.parse('BetaMuSigma(4035, 400, 2500, 6000)')
+    with pytest.raises(SystemError):
+        distributions.parse('Uniform(3, 1)')
+    with pytest.raises(NotImplementedError):         # a real OpenTURNS family without a device inverse CDF
+        distributions.parse('Gamma(2., 1., 0.)')
     kinds, params = distributions.parse_all(['Uniform(15., 60.)', 'Normal(4035., 400.)'])
-    assert kinds == [0, 1] and params == [15.0, 60.0, 4035.0, 400.0]
+    assert kinds == [0, 1] and params == [15.0, 60.0, 0.0, 0.0, 4035.0, 400.0, 0.0, 0.0]
+
+
+def test_distribution_parametrisations_against_scipy_stats():
+    """The host statement of every inverse CDF equals scipy.stats' ppf of the distribution the OpenTURNS 1.15
+    constructor describes (an independent check of parametrisation and formula); the device twins are compared
+    with the same formulas in tests/test_gpu_sobol.py."""
+    from scipy import stats
+    u = np.linspace(0.001, 0.999, 499)
+    cases = [
+        ('LogNormal(0.3, 0.6, 1.5)', stats.lognorm(s=0.6, loc=1.5, scale=np.exp(0.3))),
+        ('Triangular(1., 2., 5.)', stats.triang(c=0.25, loc=1.0, scale=4.0)),
+        ('TruncatedNormal(1., 2., -1., 2.5)', stats.truncnorm(a=-1.0, b=0.75, loc=1.0, scale=2.0)),
+        ('Beta(2.5, 4., -1., 3.)', stats.beta(2.5, 4.0, loc=-1.0, scale=4.0)),
+        ('Gumbel(2., 1.)', stats.gumbel_r(loc=1.0, scale=2.0)),
+        ('Exponential(0.5, 2.)', stats.expon(loc=2.0, scale=2.0)),
+        ('LogUniform(-1., 2.)', stats.loguniform(np.exp(-1.0), np.exp(2.0))),
+        ('WeibullMin(2., 1.5, 0.5)', stats.weibull_min(c=1.5, loc=0.5, scale=2.0)),
+        ('Logistic(1., 2.)', stats.logistic(loc=1.0, scale=2.0)),
+        ('Rayleigh(2., 1.)', stats.rayleigh(loc=1.0, scale=2.0)),
+    ]
+    for text, dist in cases:
+        d = distributions.parse(text)
+        np.testing.assert_allclose(distributions.inverse_cdf_host(d[0], d[1:], u), dist.ppf(u), rtol=1e-10, atol=1e-12,
+                                   err_msg=text)
+    # the form every shipped Channel_Flow / Mascaret case uses: mean and standard deviation on [a, b]
+    d = distributions.parse('BetaMuSigma(4031, 400, 1000, 6000).getDistribution()')
+    assert d[0] == distributions.BETA
+    ref = stats.beta(d[1], d[2], loc=d[3], scale=d[4] - d[3])
+    assert ref.mean() == pytest.approx(4031.0, rel=1e-12) and ref.std() == pytest.approx(400.0, rel=1e-12)
+    d = distributions.parse('LogNormalMuSigma(3., 1.5, 0.5).getDistribution()')
+    ref = stats.lognorm(s=d[2], loc=d[3], scale=np.exp(d[1]))
+    assert ref.mean() == pytest.approx(3.0, rel=1e-12) and ref.std() == pytest.approx(1.5, rel=1e-12)
 
 
 def test_minmax_is_sklearn_minmaxscaler():

@@ -179,7 +179,7 @@ def test_asymptotic_intervals_multi_output_and_files(tmp_path):
     w1, wt = saltelli.asymptotic_sigma_aggregated(Y, N, p)
     np.testing.assert_allclose(d['S1_agg_sigma'], w1, rtol=1e-7)
     np.testing.assert_allclose(d['ST_agg_sigma'], wt, rtol=1e-7)
-    np.testing.assert_allclose(d['mean'], Y.mean(axis=0), rtol=1e-12)
+    np.testing.assert_allclose(d['mean'], Y.mean(axis=0), rtol=1e-10)
     # the two interval estimators answer the same question
     assert np.all(d['S1_agg_sigma_jackknife'] < 3 * w1 + 1e-3) and np.all(w1 < 3 * d['S1_agg_sigma_jackknife'] + 1e-3)
     agg = json.load(open(tmp_path / 'sensitivity_aggregated.json'))

@@ -44,7 +44,7 @@ ProfScope::~ProfScope() {
 int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar, int8_t* kq,
                    int kq_scheme, double kappa, cudaStream_t st);
 int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, double kappa, long k, double* std_out,
-                     double* scratch, int* fail_flag, cudaStream_t st);
+                     int* fail_flag, cudaStream_t st);
 int launch_var(const bk_gp_s* h, int q, const double* kstar, long k, double* std_out, cudaStream_t st);
 int launch_pack_w(const double* w, int n, double* out, cudaStream_t st);
 int launch_sobol(const bk_gp_s* h, int q, const double* a, const double* b, uint64_t seed, const int* mkind,
@@ -242,8 +242,8 @@ static double pow2_at_least(double v) {
     return ldexp(1.0, e);
 }
 
-// per point: K* tile bytes (FP64 fragments or 8 int8 slices: both n_pad * 8) + 1 KiB of pass-0 scratch (int8 path)
-static size_t predict_bytes_per_point(const bk_gp_s* h) { return (size_t)h->n_pad * sizeof(double) + 1024; }
+// per point: K* tile bytes (FP64 fragments or 8 int8 slices: both n_pad * 8)
+static size_t predict_bytes_per_point(const bk_gp_s* h) { return (size_t)h->n_pad * sizeof(double); }
 
 size_t bk_gp_predict_workspace(bk_gp_t h, long k, int want_std) {
     if (!h || !want_std || k <= 0) return 0;
@@ -296,7 +296,6 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
                          per_point * PRED_CHUNK_ALIGN + 256, workspace_bytes);
     char* ws = (char*)workspace_dev;
     double* kstar = (double*)ws;                                               // or the int8 slices: same footprint
-    double* scratch = (double*)(ws + (size_t)chunk * h->n_pad * sizeof(double));
     int* fail_flag = (int*)(ws + ((workspace_bytes - 256) & ~(size_t)7));      // tail of the caller's workspace
     if (h->var_mode >= 1) BK_CUDA(cudaMemsetAsync(fail_flag, 0, sizeof(int), st));   // read back by bk_gp_predict_status
     for (long lo = 0; lo < k; lo += chunk) {
@@ -308,7 +307,7 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
                 const int scheme = h->var_mode - 1;
                 if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, nullptr, (int8_t*)kstar,
                                             scheme, kappa, st)) return rc;
-                if (int rc = launch_var_ozaki(h, q, scheme, (const int8_t*)kstar, kappa, cnt, std_dev + lo * h->m, scratch,
+                if (int rc = launch_var_ozaki(h, q, scheme, (const int8_t*)kstar, kappa, cnt, std_dev + lo * h->m,
                                               fail_flag, st)) return rc;
             } else {
                 if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, kstar, nullptr, 0, 1.0, st)) return rc;

@@ -6,6 +6,7 @@ Objects are compiled in parallel (one nvcc per .cu) and linked into
 batman_b200/libbatman_b200.so, which travels to the GPU box with the snapshot.
 """
 import os
+import re
 import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
@@ -29,9 +30,26 @@ def newest_dep():
     return max(os.path.getmtime(d) for d in deps)
 
 
-def compile_one(src):
+def header_deps(src, seen=None):
+    """Quoted includes of `src`, followed recursively (the kernels only include files of this tree)."""
+    seen = set() if seen is None else seen
+    with open(src) as f:
+        text = f.read()
+    for inc in re.findall(r'#include\s+"([^"]+)"', text):
+        path = os.path.normpath(os.path.join(os.path.dirname(src), inc))
+        if os.path.exists(path) and path not in seen:
+            seen.add(path)
+            header_deps(path, seen)
+    return seen
+
+
+def compile_one(src, force=False):
     obj = os.path.join(BUILD, src[:-3] + '.o')
     log = os.path.join(BUILD, src[:-3] + '.ptxas.log')
+    path = os.path.join(HERE, src)
+    newest = max(os.path.getmtime(d) for d in [path, os.path.abspath(__file__)] + sorted(header_deps(path)))
+    if not force and os.path.exists(obj) and os.path.getmtime(obj) >= newest:
+        return obj
     r = subprocess.run([NVCC] + FLAGS + ['-c', os.path.join(HERE, src), '-o', obj],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(log, 'w') as f:
@@ -46,7 +64,7 @@ def build(force=False):
         return OUT
     os.makedirs(BUILD, exist_ok=True)
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(compile_one, sources()))
+        objs = list(ex.map(lambda f: compile_one(f, force), sources()))
     r = subprocess.run([NVCC, '-shared', '-o', OUT] + objs + ['-lcudart'],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:

@@ -7,17 +7,22 @@
 // D_g is an int32 accumulation of int8 products (exact for n <= 16384); the 36 slice pairs with a+b <= 9
 // reproduce float64 accuracy (profiles/r01_ozaki_feasibility.md).  Same contract as k_var_trmm (gp_var.cu).
 //
-// One CTA = 128 test points.  Per row panel of W (128 rows) the K loop runs TWICE because only four
-// 128x128 int32 accumulator groups fit in TMEM (512 columns): pass 0 = groups 2..5 (slices 1..4, 10 MMAs per
-// 32-wide k slab), pass 1 = groups 6..9 (slices 1..8, 26 MMAs).  The pass-0 combination is parked in an
-// L2-resident scratch tile and added in pass 1.
-//   warp 5 lane 0 : TMA producer  (cp.async.bulk of pre-packed slice tiles, 6-slot full/empty mbarrier ring)
-//   warp 4 lane 0 : MMA issuer    (tcgen05.mma.cta_group::1.kind::i8, M128 N128 K32, SMEM descriptors, commit)
-//   warps 0..3, 6..9 : epilogue   (tcgen05.ld -> exact int64 combine -> FP64 -> sum of v^2; TMEM lanes = test points
-//                                  (M side = K* slices), columns = W rows (N side); two threads per test point, each
-//                                  draining half of the columns, software-pipelined TMEM reads, no cross-thread reduction)
+// One CTA = 128 test points (TMEM lanes, M side = K* slices) against 64-row panels of W (N side), ONE pass over
+// K per panel: all accumulator groups D_2..D_9 of the 128 x 64 tile are resident in TMEM at once, group g in columns
+// [64 (g-2), 64 (g-1)) -- 448 or 512 of the 512 columns.  The slices of a W panel are stacked along N in shared
+// memory ([slice][64 rows][32 B], 8-row core-matrix groups 256 B apart), so ONE tcgen05.mma of K* slice b against
+// W slices a..a+3 (N = 256) accumulates into the four adjacent groups a+b .. a+b+3: the instruction shape that
+// reaches the int8 peak (N = 256; an M128 instruction costs >= 94 cycles whatever N) without the 256 TMEM columns
+// per group a conventional N = 256 tile needs.  Per 32-wide k slab: 10 MMAs for the 28 pairs of the 7 x 8-bit
+// scheme (4 x N256, 2 x N192, 2 x N128, 2 x N64), 12 for the 36 pairs of the 8 x 7-bit scheme.
+//   warp 5 lane 0 : TMA producer  (cp.async.bulk of pre-packed slice tiles, 4-slot full/empty mbarrier ring;
+//                                  a slot = one k slab = the K* slices (S x 4 KiB) and the W slices (S x 2 KiB))
+//   warp 4 lane 0 : MMA issuer    (tcgen05.mma.cta_group::1.kind::i8, M128 K32, SMEM descriptors, commit)
+//   warps 0..3, 6..9 : epilogue   (tcgen05.ld -> exact int64 combine -> FP64 -> sum of v^2; two threads per test
+//                                  point, each draining 32 of the panel's 64 W rows from every group,
+//                                  software-pipelined TMEM reads, no cross-thread reduction)
 // Operand tiles are packed on the producer side (W at upload, K* by K1) in the non-swizzled K-major UMMA
-// layout: element (row r, byte b) of a 128 x 32 B tile at (r/8)*256 + (b/16)*128 + (r%8)*16 + b%16.
+// layout: element (row r, byte b) of an R x 32 B tile at (r/8)*256 + (b/16)*128 + (r%8)*16 + b%16.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -25,13 +30,15 @@
 
 namespace bk {
 
-constexpr int OZ_S = 8;                       // int8 slices per operand
-constexpr int OZ_TILE = 4096;                 // bytes of one 128 x 32 B slice tile
-constexpr int OZ_SLOTS = 6;                   // ring of 32 KiB slots (8 slice tiles each)
-constexpr int OZ_SLOT_BYTES = OZ_S * OZ_TILE; // pass 0: one slot per k slab = [A slices 1..4 | B slices 1..4]
-                                              // pass 1: two slots per k slab = [A slices 1..8], [B slices 1..8]
-constexpr int OZ_THREADS = 320;                // warps 0-3 and 6-9: epilogue (two column halves); warp 4: MMA; warp 5: TMA
-constexpr size_t OZ_SMEM = (size_t)OZ_SLOTS * OZ_SLOT_BYTES + 4 * 32 * 17 * 8 + 4 * 128 * 8 + 2 * OZ_SLOTS * 8 + 64 + 1024;
+constexpr int OZ_S = 8;                       // slice stride of both tile arrays (the 7 x 8-bit scheme leaves slot 8 unused)
+constexpr int OZ_KTILE = 4096;                // bytes of one K* slice tile: 128 test points x 32 B
+constexpr int OZ_PANEL = 64;                  // W rows per panel
+constexpr int OZ_WTILE = OZ_PANEL * 32;       // bytes of one W slice tile: 64 rows x 32 B
+constexpr int OZ_SLOTS = 4;                   // ring of 48 KiB slots: [K* slices 1..8 | W slices 1..8] of one k slab
+constexpr int OZ_SLOT_W = OZ_S * OZ_KTILE;    // offset of the W slices inside a slot
+constexpr int OZ_SLOT_BYTES = OZ_S * (OZ_KTILE + OZ_WTILE);
+constexpr int OZ_THREADS = 320;               // warps 0-3 and 6-9: epilogue (two column halves); warp 4: MMA; warp 5: TMA
+constexpr size_t OZ_SMEM = (size_t)OZ_SLOTS * OZ_SLOT_BYTES + 2 * OZ_PANEL * 8 + 2 * 128 * 8 + (2 * OZ_SLOTS + 2) * 8 + 1024;
 
 __device__ __forceinline__ uint64_t oz_desc(uint32_t smem_addr) {
     // SMEM matrix descriptor, no swizzle, K-major: LBO = 128 B (core matrices along K), SBO = 256 B (8-row groups)
@@ -63,32 +70,36 @@ __device__ __forceinline__ bool oz_wait(uint64_t* bar, uint32_t parity, int* fai
 
 // Two error-free slicings (SCHEME):
 //   0: 8 x 7-bit signed digits for both operands; group g = a + b has weight 2^-(7g-2); 36 pairs with g <= 9;
-//      pass 0 = groups 2..5, pass 1 = groups 6..9; int32 exact for n <= 16384.
+//      int32 exact for n <= 16384.
 //   1: 7 x 8-bit digits, W signed (|w| < 1/2, X = rint(w 2^55)), K* unsigned bytes (0 <= x < 1, X = rint(x 2^56));
-//      group g has weight 2^(1-8g); 28 pairs with g <= 8; pass 0 = groups 2..5, pass 1 = groups 6..8;
-//      int32 exact for n <= 8192; needs k >= 0 (c0, c1 >= 0).  22 % fewer MMAs, byte-extraction slicing in K1.
+//      group g has weight 2^(1-8g); 28 pairs with g <= 8; int32 exact for n <= 8192; needs k >= 0 (c0, c1 >= 0).
+//      22 % fewer MMAs, byte-extraction slicing in K1.
 template <int SCHEME> struct OzTraits;
 template <> struct OzTraits<0> { static constexpr int S = 8, BITS = 7, G_END = 10; };   // groups 2 .. G_END-1
 template <> struct OzTraits<1> { static constexpr int S = 7, BITS = 8, G_END = 9; };
 
-// All slice pairs (a, b), a + b = g, of the accumulator groups of one pass for one k slab, fully unrolled: per MMA
-// the issuing thread only adds a tile offset to two pre-built descriptors (start-address field, 16-B units).
-// M side (TMEM lanes) = the 128 test points (K* slices), N side (TMEM columns) = the 128 rows of the W panel.
-template <int SCHEME, int PASS>
-__device__ __forceinline__ void oz_issue_slab(uint32_t tmem_base, uint64_t kdesc0, uint64_t wdesc0, uint32_t idesc,
-                                              uint32_t not_first) {
-    constexpr int S = OzTraits<SCHEME>::S;
-    constexpr int G_LO = PASS == 0 ? 2 : 6, G_HI = PASS == 0 ? 6 : OzTraits<SCHEME>::G_END;
+// instruction descriptor: S32 accumulate; A = K* slices (signed, or unsigned bytes in scheme 1), B = W slices
+// (signed); K-major both; M = 128, N = 64 * (stacked W slices)
+template <int SCHEME>
+__device__ __forceinline__ constexpr uint32_t oz_idesc(int n) {
+    return (2u << 4) | ((SCHEME == 0 ? 1u : 0u) << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// All slice pairs of one k slab, fully unrolled: K* slice b against the stacked W slices a .. a+3 lands in the
+// adjacent accumulator groups a+b .. a+b+3.  Per MMA the issuing thread only adds a tile offset to two pre-built
+// descriptors (start-address field, 16-B units).  The two b = 1 instructions touch every group first: they
+// overwrite on the first slab of a panel (`not_first` = 0), everything else accumulates.
+template <int SCHEME>
+__device__ __forceinline__ void oz_issue_slab(uint32_t tmem_base, uint64_t kdesc0, uint64_t wdesc0, uint32_t not_first) {
+    constexpr int S = OzTraits<SCHEME>::S, G_END = OzTraits<SCHEME>::G_END;
 #pragma unroll
-    for (int g = G_LO; g < G_HI; ++g) {
+    for (int b = 1; b <= S; ++b) {
+        const int a_max = G_END - 1 - b < S ? G_END - 1 - b : S;
 #pragma unroll
-        for (int a = 1; a <= S; ++a) {
-            const int b = g - a;                       // a = W slice, b = K* slice
-            if (b >= 1 && b <= S) {
-                const bool first_of_group = (a == (g - S > 1 ? g - S : 1));
-                oz_mma(tmem_base + (uint32_t)(g - G_LO) * 128, kdesc0 + (uint64_t)((b - 1) * (OZ_TILE >> 4)),
-                       wdesc0 + (uint64_t)((a - 1) * (OZ_TILE >> 4)), idesc, first_of_group ? not_first : 1u);
-            }
+        for (int a = 1; a <= a_max; a += 4) {
+            const int cnt = a_max - a + 1 < 4 ? a_max - a + 1 : 4;
+            oz_mma(tmem_base + (uint32_t)((a + b - 2) * OZ_PANEL), kdesc0 + (uint64_t)((b - 1) * (OZ_KTILE >> 4)),
+                   wdesc0 + (uint64_t)((a - 1) * (OZ_WTILE >> 4)), oz_idesc<SCHEME>(cnt * OZ_PANEL), b == 1 ? not_first : 1u);
         }
     }
 }
@@ -97,18 +108,28 @@ __device__ __forceinline__ double oz_i64_to_double(long long h) {    // exact fo
     return __longlong_as_double(h + 0x4338000000000000ll) - 6755399441055744.0;
 }
 
+template <int NG>
+__device__ __forceinline__ void oz_load_chunk(uint32_t (&d)[NG][8], uint32_t taddr) {
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(d[g][0]), "=r"(d[g][1]), "=r"(d[g][2]), "=r"(d[g][3]), "=r"(d[g][4]), "=r"(d[g][5]),
+                       "=r"(d[g][6]), "=r"(d[g][7])
+                     : "r"(taddr + (uint32_t)(g * OZ_PANEL)));
+}
+
 template <int SCHEME>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, const int8_t* __restrict__ kq,
-            int n_pad, double kappa, double kdiag, double y_std, double* __restrict__ scratch,
-            double* __restrict__ std_out, long k, int ld, int q, int* __restrict__ fail_flag) {
-    constexpr int S = OzTraits<SCHEME>::S, BITS = OzTraits<SCHEME>::BITS;
-    constexpr int NG1 = OzTraits<SCHEME>::G_END - 6;                 // accumulator groups of pass 1 (4 or 3)
+            int n_pad, double kappa, double kdiag, double y_std, double* __restrict__ std_out, long k, int ld, int q,
+            int* __restrict__ fail_flag) {
+    constexpr int S = OzTraits<SCHEME>::S;
+    constexpr int NG = OzTraits<SCHEME>::G_END - 2;                  // accumulator groups (8 or 7)
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* stages = smem;
-    double* red = reinterpret_cast<double*>(smem + (size_t)OZ_SLOTS * OZ_SLOT_BYTES);         // [128] row scales (+ spare)
-    double* colred = red + 4 * 32 * 17;                                                       // [128]
-    uint64_t* full = reinterpret_cast<uint64_t*>(colred + 4 * 128);                           // [slots]
+    double* sigs = reinterpret_cast<double*>(smem + (size_t)OZ_SLOTS * OZ_SLOT_BYTES);        // [2][64] sigma_i * kappa
+    double* colred = sigs + 2 * OZ_PANEL;                                                     // [2][128]
+    uint64_t* full = reinterpret_cast<uint64_t*>(colred + 2 * 128);                           // [slots]
     uint64_t* empty = full + OZ_SLOTS;                                                        // [slots]
     uint64_t* acc_full = empty + OZ_SLOTS;
     uint64_t* acc_empty = acc_full + 1;
@@ -116,9 +137,8 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
     __shared__ volatile int fail_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_panels = n_pad / 128, nks = n_pad / 32;
-    const int8_t* kt = kq + (size_t)blockIdx.x * nks * OZ_S * OZ_TILE;
-    double* scr = scratch + (size_t)blockIdx.x * 128 * 128;
+    const int n_panels = n_pad / OZ_PANEL, nks = n_pad / 32;
+    const int8_t* kt = kq + (size_t)blockIdx.x * nks * OZ_S * OZ_KTILE;
 
     if (tid == 0) {
         for (int s = 0; s < OZ_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -137,155 +157,102 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
     const uint32_t tmem_base = tmem_base_s;
 
     if (warp == 5) {
-        // ================= TMA producer =================
+        // ================= TMA producer: W is lower triangular, panel P needs the k slabs below 2 (P + 1) =================
         if (lane == 0) {
             int fail = 0;
             long u = 0;                                                      // running slot-use counter
-            auto fill = [&](const int8_t* a_src, uint32_t a_bytes, const int8_t* b_src, uint32_t b_bytes) -> bool {
-                const int s = (int)(u % OZ_SLOTS);
-                if (u >= OZ_SLOTS && !oz_wait(&empty[s], (uint32_t)(((u / OZ_SLOTS) - 1) & 1), &fail, &fail_s)) return false;
-                unsigned char* dst = stages + (size_t)s * OZ_SLOT_BYTES;
-                mbar_expect_tx(&full[s], a_bytes + b_bytes);
-                tma_load_1d(dst, a_src, a_bytes, &full[s]);
-                if (b_bytes) tma_load_1d(dst + a_bytes, b_src, b_bytes, &full[s]);
-                ++u;
-                return true;
-            };
             for (int panel = 0; panel < n_panels && !fail; ++panel)
-                for (int pass = 0; pass < 2 && !fail; ++pass)
-                    for (int ks = 0; ks < (panel + 1) * 4 && !fail; ++ks) {
-                        const int8_t* a_src = wq + ((size_t)panel * nks + ks) * OZ_S * OZ_TILE;
-                        const int8_t* b_src = kt + (size_t)ks * OZ_S * OZ_TILE;
-                        if (pass == 0) {
-                            fill(a_src, 4 * OZ_TILE, b_src, 4 * OZ_TILE);
-                        } else {
-                            if (fill(a_src, S * OZ_TILE, nullptr, 0)) fill(b_src, S * OZ_TILE, nullptr, 0);
-                        }
-                    }
+                for (int ks = 0; ks < (panel + 1) * 2; ++ks, ++u) {
+                    const int s = (int)(u % OZ_SLOTS);
+                    if (u >= OZ_SLOTS && !oz_wait(&empty[s], (uint32_t)(((u / OZ_SLOTS) - 1) & 1), &fail, &fail_s)) break;
+                    unsigned char* dst = stages + (size_t)s * OZ_SLOT_BYTES;
+                    mbar_expect_tx(&full[s], (uint32_t)(S * (OZ_KTILE + OZ_WTILE)));
+                    tma_load_1d(dst, kt + (size_t)ks * OZ_S * OZ_KTILE, S * OZ_KTILE, &full[s]);
+                    tma_load_1d(dst + OZ_SLOT_W, wq + ((size_t)panel * nks + ks) * OZ_S * OZ_WTILE, S * OZ_WTILE, &full[s]);
+                }
             if (fail) fail_s = 1;
         }
     } else if (warp == 4) {
         // ================= MMA issuer =================
         if (lane == 0) {
             int fail = 0;
-            // instruction descriptor: S32 accumulate; A = K* slices (signed, or unsigned bytes in scheme 1), B = W slices
-            // (signed); K-major both; N = 128, M = 128
-            const uint32_t idesc = (2u << 4) | ((SCHEME == 0 ? 1u : 0u) << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
             long u = 0;
-            int round = 0;                                                   // (panel, pass) counter
-            for (int panel = 0; panel < n_panels && !fail; ++panel)
-                for (int pass = 0; pass < 2 && !fail; ++pass, ++round) {
-                    if (round > 0 && !oz_wait(acc_empty, (uint32_t)((round - 1) & 1), &fail, &fail_s)) break;
+            for (int panel = 0; panel < n_panels && !fail; ++panel) {
+                if (panel > 0 && !oz_wait(acc_empty, (uint32_t)((panel - 1) & 1), &fail, &fail_s)) break;
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int ks = 0; ks < (panel + 1) * 2; ++ks, ++u) {
+                    const int s = (int)(u % OZ_SLOTS);
+                    if (!oz_wait(&full[s], (uint32_t)((u / OZ_SLOTS) & 1), &fail, &fail_s)) break;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const int nks_p = (panel + 1) * 4;
-                    for (int ks = 0; ks < nks_p; ++ks) {
-                        const int s0 = (int)(u % OZ_SLOTS), s1 = (int)((u + 1) % OZ_SLOTS);
-                        if (!oz_wait(&full[s0], (uint32_t)((u / OZ_SLOTS) & 1), &fail, &fail_s)) break;
-                        if (pass == 1 && !oz_wait(&full[s1], (uint32_t)(((u + 1) / OZ_SLOTS) & 1), &fail, &fail_s)) break;
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t w_base = smem_u32(stages + (size_t)s0 * OZ_SLOT_BYTES);
-                        const uint32_t k_base = pass == 0 ? w_base + 4 * OZ_TILE : smem_u32(stages + (size_t)s1 * OZ_SLOT_BYTES);
-                        if (pass == 0) oz_issue_slab<SCHEME, 0>(tmem_base, oz_desc(k_base), oz_desc(w_base), idesc, ks > 0 ? 1u : 0u);
-                        else oz_issue_slab<SCHEME, 1>(tmem_base, oz_desc(k_base), oz_desc(w_base), idesc, ks > 0 ? 1u : 0u);
-                        oz_commit(&empty[s0]);                               // slot(s) free once these MMAs retire
-                        if (pass == 1) oz_commit(&empty[s1]);
-                        u += pass == 0 ? 1 : 2;
-                    }
-                    oz_commit(acc_full);                                     // accumulators of this (panel, pass) complete
+                    const uint32_t k_base = smem_u32(stages + (size_t)s * OZ_SLOT_BYTES);
+                    oz_issue_slab<SCHEME>(tmem_base, oz_desc(k_base), oz_desc(k_base + OZ_SLOT_W), ks > 0 ? 1u : 0u);
+                    oz_commit(&empty[s]);                                    // slot free once these MMAs retire
                 }
+                oz_commit(acc_full);                                         // accumulators of this panel complete
+            }
             if (fail) fail_s = 1;
         }
     } else {
-        // ================= epilogue: warps 0..3 drain W-row columns 0..63 of every group, warps 6..9 columns 64..127.
-        // A warp may only touch TMEM lanes 32*(warp%4)..+31, so thread (warp%4, lane) owns test point 32*(warp%4)+lane.
+        // ================= epilogue: warps 0..3 drain W rows 0..31 of the panel from every group, warps 6..9 rows
+        // 32..63.  A warp may only touch TMEM lanes 32*(warp%4)..+31, so thread (warp%4, lane) owns test point
+        // 32*(warp%4)+lane.
         int fail = 0;
         double vsum = 0.0;                                  // sum over this thread's W rows of v^2 for its test point
         const int half = warp < 4 ? 0 : 1;
         const int tp = (warp & 3) * 32 + lane;
-        double* sigs = red;                                 // [128] sigma_i * kappa of the current panel
-        const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-        int round = 0;
-        auto load_chunk = [&](uint32_t (&d)[4][16], int c, int ng) {
+        const uint32_t col_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32);
+        auto process_chunk = [&](const uint32_t (&d)[NG][8], const double* sg) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                if (g < ng) {
-                    const uint32_t taddr = lane_base + (uint32_t)(g * 128 + c * 16);
-                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                                 "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                                 : "=r"(d[g][0]), "=r"(d[g][1]), "=r"(d[g][2]), "=r"(d[g][3]), "=r"(d[g][4]),
-                                   "=r"(d[g][5]), "=r"(d[g][6]), "=r"(d[g][7]), "=r"(d[g][8]), "=r"(d[g][9]),
-                                   "=r"(d[g][10]), "=r"(d[g][11]), "=r"(d[g][12]), "=r"(d[g][13]), "=r"(d[g][14]),
-                                   "=r"(d[g][15])
-                                 : "r"(taddr));
+            for (int j = 0; j < 8; ++j) {
+                // Combine the groups EXACTLY in int64 (weights 2^-BITS apart) in two parts, then integer add + DADD
+                // converts to FP64 (I2F.F64 is slow).
+                double hi, lo;
+                if constexpr (SCHEME == 0) {             // |D| < 2^29: 21 + 29 < 51 bits; groups 5 / 9: 2^-33 / 2^-61
+                    hi = oz_i64_to_double(((long long)(int)d[0][j] << 21) + ((long long)(int)d[1][j] << 14) +
+                                          ((long long)(int)d[2][j] << 7) + (long long)(int)d[3][j]) * 0x1p-33;
+                    lo = oz_i64_to_double(((long long)(int)d[4][j] << 21) + ((long long)(int)d[5][j] << 14) +
+                                          ((long long)(int)d[6][j] << 7) + (long long)(int)d[7][j]) * 0x1p-61;
+                } else {                                 // |D| < 2^31: groups 2..5 as two exact halves 2^16 apart
+                    const double ha = oz_i64_to_double(((long long)(int)d[0][j] << 8) + (long long)(int)d[1][j]);
+                    const double hb = oz_i64_to_double(((long long)(int)d[2][j] << 8) + (long long)(int)d[3][j]);
+                    hi = fma(ha, 0x1p16, hb) * 0x1p-39;  // group 5 weight 2^(1-40)
+                    lo = oz_i64_to_double(((long long)(int)d[4][j] << 16) + ((long long)(int)d[5][j] << 8) +
+                                          (long long)(int)d[6][j]) * 0x1p-63;     // groups 6..8: 16 + 31 < 51 bits
                 }
+                const double v = sg[j] * (lo + hi);
+                vsum = fma(v, v, vsum);
             }
         };
-        auto process_chunk = [&](const uint32_t (&d)[4][16], int c, int pass) {
-            double sv[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) sv[j] = pass == 1 ? scr[(size_t)(c * 16 + j) * 128 + tp] : 0.0;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                // Combine the groups of the pass EXACTLY in int64 (weights 2^-BITS apart), then integer add + DADD
-                // converts to FP64 (I2F.F64 is slow).  The scale of the LAST group of the pass applies.
-                double h;
-                if (pass == 0) {
-                    if constexpr (SCHEME == 0) {         // |D| < 2^29: 21 + 29 < 51 bits
-                        h = oz_i64_to_double(((long long)(int)d[0][j] << 21) + ((long long)(int)d[1][j] << 14) +
-                                             ((long long)(int)d[2][j] << 7) + (long long)(int)d[3][j]) * 0x1p-33;
-                    } else {                             // |D| < 2^31: two exact halves, 2^16 apart; group 5 weight 2^(1-40)
-                        const double ha = oz_i64_to_double(((long long)(int)d[0][j] << 8) + (long long)(int)d[1][j]);
-                        const double hb = oz_i64_to_double(((long long)(int)d[2][j] << 8) + (long long)(int)d[3][j]);
-                        h = fma(ha, 0x1p16, hb) * 0x1p-39;
-                    }
-                    scr[(size_t)(c * 16 + j) * 128 + tp] = h;
-                } else {
-                    if constexpr (SCHEME == 0) {
-                        h = oz_i64_to_double(((long long)(int)d[0][j] << 21) + ((long long)(int)d[1][j] << 14) +
-                                             ((long long)(int)d[2][j] << 7) + (long long)(int)d[3][j]) * 0x1p-61;
-                    } else {                             // groups 6..8: 16 + 31 < 51 bits; group 8 weight 2^(1-64)
-                        h = oz_i64_to_double(((long long)(int)d[0][j] << 16) + ((long long)(int)d[1][j] << 8) +
-                                             (long long)(int)d[2][j]) * 0x1p-63;
-                    }
-                    const double v = sigs[c * 16 + j] * (h + sv[j]);
-                    vsum = fma(v, v, vsum);
-                }
-            }
-        };
-        // After a fault the loop keeps its shape (every epilogue warp meets the named barriers the same number of
+        // After a fault the loop keeps its shape (every epilogue warp meets the named barrier the same number of
         // times) and only the work is skipped.
-        for (int panel = 0; panel < n_panels; ++panel)
-            for (int pass = 0; pass < 2; ++pass, ++round) {
-                if (pass == 1) {
-                    // named barrier among the 8 epilogue warps: previous panel's sigs fully consumed, then refill
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if (half == 0) sigs[tp] = wsig[panel * 128 + tp] * kappa;
-                    asm volatile("bar.sync 1, 256;" ::: "memory");
-                }
-                if (!oz_wait(acc_full, (uint32_t)(round & 1), &fail, &fail_s)) continue;
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                // 4 chunks of 16 W rows per half, software pipelined: the TMEM read of chunk c+1 flies under the
-                // arithmetic of chunk c (tcgen05.wait::ld waits for everything issued so far)
-                const int ng = pass == 0 ? 4 : NG1;
-                const int c0 = half * 4;
-                uint32_t da[4][16], db[4][16];
-                load_chunk(da, c0, ng);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                load_chunk(db, c0 + 1, ng);
-                process_chunk(da, c0, pass);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                load_chunk(da, c0 + 2, ng);
-                process_chunk(db, c0 + 1, pass);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                load_chunk(db, c0 + 3, ng);
-                process_chunk(da, c0 + 2, pass);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // every TMEM read of this round is complete: release the accumulators before the last arithmetic
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty);
-                process_chunk(db, c0 + 3, pass);
-            }
+        for (int panel = 0; panel < n_panels; ++panel) {
+            // row scales of this panel, double buffered: one named barrier per panel among the 8 epilogue warps
+            double* sg = sigs + (panel & 1) * OZ_PANEL;
+            if (half == 0 && tp < OZ_PANEL) sg[tp] = wsig[panel * OZ_PANEL + tp] * kappa;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (!oz_wait(acc_full, (uint32_t)(panel & 1), &fail, &fail_s)) continue;
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // 4 chunks of 8 W rows, software pipelined: the TMEM read of chunk c+1 flies under the arithmetic of
+            // chunk c (tcgen05.wait::ld waits for everything issued so far)
+            const double* sgh = sg + half * 32;
+            uint32_t da[NG][8], db[NG][8];
+            oz_load_chunk<NG>(da, col_base);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            oz_load_chunk<NG>(db, col_base + 8);
+            process_chunk(da, sgh);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            oz_load_chunk<NG>(da, col_base + 16);
+            process_chunk(db, sgh + 8);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            oz_load_chunk<NG>(db, col_base + 24);
+            process_chunk(da, sgh + 16);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // every TMEM read of this panel is complete: release the accumulators before the last arithmetic
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+            process_chunk(db, sgh + 24);
+        }
         if (fail) fail_s = 1;
         colred[half * 128 + tp] = vsum;
     }
@@ -323,18 +290,18 @@ __global__ void k_slice_w(const double* __restrict__ src, int n, int ld, int tra
     if (mx > 0.0) { frexp(mx, &e); sig = ldexp(1.0, e + (scheme == 1 ? 1 : 0)); }   // |w|/sig < 1 (scheme 0) or < 1/2 (scheme 1)
     if (lane == 0) wsig[row] = sig;
     const double inv = 1.0 / sig;                           // power of two: exact
-    const int panel = row >> 7, r = row & 127;
+    const int panel = row / OZ_PANEL, r = row % OZ_PANEL;      // tile (panel, k slab, slice): 64 rows x 32 B
     for (int j = lane; j < n_pad; j += 32) {
         double w = 0.0;
         if (row < n && j <= row) w = (transposed ? src[(size_t)j * ld + row] : src[(size_t)row * ld + j]) * inv;
         const int ks = j >> 5, b = j & 31;
-        int8_t* base = wq + ((size_t)panel * nks + ks) * OZ_S * OZ_TILE + (r >> 3) * 256 + (b >> 4) * 128 + (r & 7) * 16 + (b & 15);
+        int8_t* base = wq + ((size_t)panel * nks + ks) * OZ_S * OZ_WTILE + (r >> 3) * 256 + (b >> 4) * 128 + (r & 7) * 16 + (b & 15);
         if (scheme == 0) {                                  // 8 x 7-bit digits, greedy from the top (all exact in FP64)
             double y = w * 64.0;
 #pragma unroll
             for (int a = 0; a < 8; ++a) {
                 const double qd = rint(y);
-                base[(size_t)a * OZ_TILE] = (int8_t)(int)qd;
+                base[(size_t)a * OZ_WTILE] = (int8_t)(int)qd;
                 y = (y - qd) * 128.0;                       // exact: |y - qd| <= 1/2
             }
         } else {                                            // 7 signed base-256 digits of X = rint(w 2^55), |X| < 2^54
@@ -342,11 +309,11 @@ __global__ void k_slice_w(const double* __restrict__ src, int n, int ld, int tra
 #pragma unroll
             for (int a = 6; a >= 1; --a) {
                 const long long dg = ((X + 128) & 255) - 128;
-                base[(size_t)a * OZ_TILE] = (int8_t)dg;
+                base[(size_t)a * OZ_WTILE] = (int8_t)dg;
                 X = (X - dg) >> 8;
             }
             base[0] = (int8_t)X;                            // |X| <= 64
-            base[(size_t)7 * OZ_TILE] = 0;
+            base[(size_t)7 * OZ_WTILE] = 0;
         }
     }
 }
@@ -360,7 +327,7 @@ int launch_slice_w(const double* src, int n, int ld, int transposed, int scheme,
 }
 
 int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, double kappa, long k, double* std_out,
-                     double* scratch, int* fail_flag, cudaStream_t st) {
+                     int* fail_flag, cudaStream_t st) {
     const GpOutput& o = h->out[q];
     if (!o.wq || !o.wsig) return set_error("int8 variance path requested but output %d has no sliced L^-1", q);
     static OncePerDevice attr_set;
@@ -371,10 +338,10 @@ int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, doub
     const unsigned grid = (unsigned)((k + 127) / 128);
     ProfScope prof(PROF_VAR, st);
     if (scheme == 1)
-        k_var_ozaki<1><<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std, scratch,
+        k_var_ozaki<1><<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std,
                                                           std_out, k, h->m, q, fail_flag);
     else
-        k_var_ozaki<0><<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std, scratch,
+        k_var_ozaki<0><<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std,
                                                           std_out, k, h->m, q, fail_flag);
     BK_LAUNCH_CHECK("k_var_ozaki");
     return 0;

@@ -162,6 +162,20 @@ int bk_gp_create(bk_gp_t* out, int n, int p, int m) {
 }
 
 int bk_gp_destroy(bk_gp_t h) {
+    if (h && h->lanes) {
+        PredictLanes* L = h->lanes;
+        int cur = 0;
+        const bool sw = cudaGetDevice(&cur) == cudaSuccess && cur != L->device && cudaSetDevice(L->device) == cudaSuccess;
+        if (L->k1) { cudaStreamSynchronize(L->k1); cudaStreamDestroy(L->k1); }
+        if (L->k2) { cudaStreamSynchronize(L->k2); cudaStreamDestroy(L->k2); }
+        if (L->fork) cudaEventDestroy(L->fork);
+        for (int i = 0; i < 2; ++i) {
+            if (L->k1done[i]) cudaEventDestroy(L->k1done[i]);
+            if (L->k2done[i]) cudaEventDestroy(L->k2done[i]);
+        }
+        if (sw) cudaSetDevice(cur);
+        delete L;
+    }
     delete h;
     return 0;
 }
@@ -245,12 +259,54 @@ static double pow2_at_least(double v) {
 // per point: K* tile bytes (FP64 fragments or 8 int8 slices: both n_pad * 8)
 static size_t predict_bytes_per_point(const bk_gp_s* h) { return (size_t)h->n_pad * sizeof(double); }
 
+// A sigma prediction is a sequence of units (chunk of points, output): K1 writes the K* tiles of the unit, the sigma
+// kernel consumes them.  With two K* buffers K1 of unit u+1 runs beside the sigma kernel of unit u.
 size_t bk_gp_predict_workspace(bk_gp_t h, long k, int want_std) {
     if (!h || !want_std || k <= 0) return 0;
     long kk = (k + PRED_CHUNK_ALIGN - 1) / PRED_CHUNK_ALIGN * PRED_CHUNK_ALIGN;
-    const long cap = 148L * TILE_T * 8;   // 8 test tiles per SM per chunk: 16 warps/SM for K1, 8 waves for K2
+    const long cap = 148L * TILE_T * 8;   // 8 test tiles per SM per chunk: 8 waves of the sigma kernel
+    const bool several_units = kk > cap || h->m > 1;
     if (kk > cap) kk = cap;
-    return (size_t)kk * predict_bytes_per_point(h) + 256;
+    return (size_t)kk * predict_bytes_per_point(h) * (several_units ? 2 : 1) + 256;
+}
+
+static int lanes_get(bk_gp_s* h) {
+    int dev = 0;
+    BK_CUDA(cudaGetDevice(&dev));
+    if (h->lanes && h->lanes->device == dev) return 0;
+    if (h->lanes) return set_error("bk_gp_predict: handle was first used on device %d, now on %d", h->lanes->device, dev);
+    PredictLanes* L = new (std::nothrow) PredictLanes();
+    if (!L) return set_error("bk_gp_predict: out of host memory");
+    h->lanes = L;                    // owned by the handle from here on (bk_gp_destroy releases partial state too)
+    L->device = dev;
+    int least = 0, greatest = 0;
+    BK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    // the sigma kernel needs a whole SM's shared memory per CTA: its CTAs go first whenever an SM frees up, K1 fills
+    // the registers and shared memory left beside them
+    BK_CUDA(cudaStreamCreateWithPriority(&L->k1, cudaStreamNonBlocking, least));
+    BK_CUDA(cudaStreamCreateWithPriority(&L->k2, cudaStreamNonBlocking, greatest));
+    BK_CUDA(cudaEventCreateWithFlags(&L->fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        BK_CUDA(cudaEventCreateWithFlags(&L->k1done[i], cudaEventDisableTiming));
+        BK_CUDA(cudaEventCreateWithFlags(&L->k2done[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+// K1 then the sigma kernel of one unit, each on the stream of its lane
+static int predict_unit(bk_gp_s* h, int q, const double* pts, long cnt, double* mean, double* std_out, double* kstar,
+                        int* fail_flag, cudaStream_t s1, cudaStream_t s2, cudaEvent_t between) {
+    if (h->var_mode >= 1) {
+        const GpOutput& o = h->out[q];
+        const double kappa = pow2_at_least(o.kmax * 1.000001);   // |k| <= (|c0| + |c1| or sum |coef_t|)(1 + few eps) < kappa
+        const int scheme = h->var_mode - 1;
+        if (int rc = launch_predict(h, q, pts, cnt, mean, nullptr, (int8_t*)kstar, scheme, kappa, s1)) return rc;
+        if (between) { BK_CUDA(cudaEventRecord(between, s1)); BK_CUDA(cudaStreamWaitEvent(s2, between, 0)); }
+        return launch_var_ozaki(h, q, scheme, (const int8_t*)kstar, kappa, cnt, std_out, fail_flag, s2);
+    }
+    if (int rc = launch_predict(h, q, pts, cnt, mean, kstar, nullptr, 0, 1.0, s1)) return rc;
+    if (between) { BK_CUDA(cudaEventRecord(between, s1)); BK_CUDA(cudaStreamWaitEvent(s2, between, 0)); }
+    return launch_var(h, q, kstar, cnt, std_out, s2);
 }
 
 int bk_gp_set_output_int8(bk_gp_t h, int q, const int8_t* wq_dev, const double* wsig_dev) {
@@ -258,6 +314,12 @@ int bk_gp_set_output_int8(bk_gp_t h, int q, const int8_t* wq_dev, const double* 
     if (q < 0 || q >= h->m) return set_error("bk_gp_set_output_int8: output %d out of range [0, %d)", q, h->m);
     h->out[q].wq = wq_dev;
     h->out[q].wsig = wsig_dev;
+    return 0;
+}
+
+int bk_gp_set_overlap(bk_gp_t h, int on) {
+    if (!h) return set_error("bk_gp_set_overlap: NULL handle");
+    h->overlap = on != 0;
     return 0;
 }
 
@@ -290,31 +352,50 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
         return 0;
     }
     const size_t per_point = predict_bytes_per_point(h);
-    long chunk = workspace_bytes > 256 ? (long)((workspace_bytes - 256) / per_point) / PRED_CHUNK_ALIGN * PRED_CHUNK_ALIGN : 0;
-    if (!workspace_dev || chunk < PRED_CHUNK_ALIGN)
+    const long fit = workspace_bytes > 256 ? (long)((workspace_bytes - 256) / per_point) : 0;   // points of K* the workspace holds
+    if (!workspace_dev || fit < PRED_CHUNK_ALIGN)
         return set_error("bk_gp_predict: sigma needs a workspace of at least %zu bytes (got %zu)",
                          per_point * PRED_CHUNK_ALIGN + 256, workspace_bytes);
     char* ws = (char*)workspace_dev;
-    double* kstar = (double*)ws;                                               // or the int8 slices: same footprint
     int* fail_flag = (int*)(ws + ((workspace_bytes - 256) & ~(size_t)7));      // tail of the caller's workspace
     if (h->var_mode >= 1) BK_CUDA(cudaMemsetAsync(fail_flag, 0, sizeof(int), st));   // read back by bk_gp_predict_status
+    // two K* buffers whenever the call has several units and the workspace holds two chunks
+    const long k_al = (k + PRED_CHUNK_ALIGN - 1) / PRED_CHUNK_ALIGN * PRED_CHUNK_ALIGN;
+    long chunk = fit / PRED_CHUNK_ALIGN * PRED_CHUNK_ALIGN;
+    int nbuf = 1;
+    if (h->overlap && (k_al > chunk || h->m > 1)) {
+        const long half = fit / 2 / PRED_CHUNK_ALIGN * PRED_CHUNK_ALIGN;
+        if (half >= PRED_CHUNK_ALIGN) { chunk = half; nbuf = 2; }
+    }
+    if (chunk > k_al) chunk = k_al;
+    double* kbuf[2] = {(double*)ws, (double*)(ws + (size_t)chunk * per_point)};
+    if (nbuf == 1) {
+        for (long lo = 0; lo < k; lo += chunk) {
+            const long cnt = (k - lo) < chunk ? (k - lo) : chunk;
+            for (int q = 0; q < h->m; ++q)
+                if (int rc = predict_unit(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, std_dev + lo * h->m,
+                                          kbuf[0], fail_flag, st, st, nullptr)) return rc;
+        }
+        return 0;
+    }
+    if (int rc = lanes_get(h)) return rc;
+    PredictLanes* L = h->lanes;
+    BK_CUDA(cudaEventRecord(L->fork, st));
+    BK_CUDA(cudaStreamWaitEvent(L->k1, L->fork, 0));
+    BK_CUDA(cudaStreamWaitEvent(L->k2, L->fork, 0));
+    long u = 0;
     for (long lo = 0; lo < k; lo += chunk) {
         const long cnt = (k - lo) < chunk ? (k - lo) : chunk;
-        for (int q = 0; q < h->m; ++q) {
-            if (h->var_mode >= 1) {
-                const GpOutput& o = h->out[q];
-                const double kappa = pow2_at_least(o.kmax * 1.000001);   // |k| <= (|c0| + |c1| or sum |coef_t|)(1 + few eps) < kappa
-                const int scheme = h->var_mode - 1;
-                if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, nullptr, (int8_t*)kstar,
-                                            scheme, kappa, st)) return rc;
-                if (int rc = launch_var_ozaki(h, q, scheme, (const int8_t*)kstar, kappa, cnt, std_dev + lo * h->m,
-                                              fail_flag, st)) return rc;
-            } else {
-                if (int rc = launch_predict(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, kstar, nullptr, 0, 1.0, st)) return rc;
-                if (int rc = launch_var(h, q, kstar, cnt, std_dev + lo * h->m, st)) return rc;
-            }
+        for (int q = 0; q < h->m; ++q, ++u) {
+            const int b = (int)(u & 1);
+            if (u >= 2) BK_CUDA(cudaStreamWaitEvent(L->k1, L->k2done[b], 0));   // the sigma kernel of unit u-2 released K* buffer b
+            if (int rc = predict_unit(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, std_dev + lo * h->m,
+                                      kbuf[b], fail_flag, L->k1, L->k2, L->k1done[b])) return rc;
+            BK_CUDA(cudaEventRecord(L->k2done[b], L->k2));
         }
     }
+    // join: the last sigma kernel follows every K1 (through k1done) and every earlier sigma kernel (stream order)
+    BK_CUDA(cudaStreamWaitEvent(st, L->k2done[(int)((u - 1) & 1)], 0));
     return 0;
 }
 

@@ -1,5 +1,6 @@
 // Host-side model handle behind the C ABI (include/batman_b200.h).
 #pragma once
+#include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <vector>
@@ -43,9 +44,19 @@ struct GpOutput {
 
 }  // namespace bk
 
+// Two internal streams of a sigma prediction: K1 of unit u+1 (FP64 pipe) runs beside the sigma kernel of unit u
+// (tensor pipe) on double-buffered K* workspaces.  Created on first use, on the device current at that time.
+struct PredictLanes {
+    cudaStream_t k1 = nullptr, k2 = nullptr;
+    cudaEvent_t fork = nullptr, k1done[2] = {nullptr, nullptr}, k2done[2] = {nullptr, nullptr};
+    int device = -1;
+};
+
 struct bk_gp_s {
     int n = 0, p = 0, P = 0, m = 0, n_pad = 0;
-    int var_mode = 0;                // 0 = FP64 DMMA (k_var_trmm), 1 = int8 tcgen05 (k_var_ozaki)
+    int var_mode = 0;                // 0 = FP64 DMMA (k_var_trmm), 1 / 2 = int8 tcgen05 (k_var_ozaki, scheme 0 / 1)
+    PredictLanes* lanes = nullptr;
+    bool overlap = true;             // bk_gp_set_overlap: K1 of unit u+1 beside the sigma kernel of unit u
     double scale[bk::MAX_P];
     double mn[bk::MAX_P];
     std::vector<bk::GpOutput> out;

@@ -191,7 +191,8 @@ class DeviceModel:
                 self.check_pipeline_flag()
         return mean, std
 
-    E2E_CHUNK = 2 * 148 * 128 * 8     # rows per pipelined host slice (two K* chunks of 151 552 rows)
+    E2E_CHUNK = 4 * 148 * 128 * 8     # rows per pipelined host slice (four K* chunks of 151 552 rows: inside a slice
+                                      # K1 of chunk c+1 overlaps the sigma kernel of chunk c)
 
     def predict(self, points, return_std=True):
         """numpy in, numpy out (the Kriging.evaluate boundary): host<->device copies included.

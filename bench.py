@@ -666,10 +666,12 @@ def main():
     int8 = model.sigma_kernel == 'int8'
     n_panels = (N_TRAIN + 127) // 128
     if int8:
-        # executed int8 work of k_var_ozaki: 28 (7x8-bit scheme) or 36 (8x7-bit) slice-pair MMAs (M128 N128 K32) per
-        # 32-wide k slab, 2 nP (nP+1) slabs per tile of 128 rows  (== ncu sm__ops_path_tensor_op_utcimma_src_int8)
+        # executed int8 work of k_var_ozaki: 28 (7x8-bit scheme) or 36 (8x7-bit) slice pairs, each 128 test points x
+        # 64 W rows x 32 k per slab; W is lower triangular, so the 64-row panel P runs 2 (P + 1) slabs: nP64 (nP64 + 1)
+        # slabs per tile of 128 test points  (== ncu sm__ops_path_tensor_op_utcimma_src_int8)
         pairs = 28 if getattr(model, 'int8_scheme', 0) == 1 else 36
-        int8_ops_per_row = pairs * 2.0 * 128 * 128 * 32 * 2 * n_panels * (n_panels + 1) / 128
+        n_p64 = 2 * n_panels
+        int8_ops_per_row = pairs * 2.0 * 128 * 64 * 32 * n_p64 * (n_p64 + 1) / 128
         achieved = int8_ops_per_row * rows_per_launch / avg_var_s * 1e-12
         peak, r_unit = INT8_PEAK_TOPS, "TOP/s"
         kernel_name = "k_var_ozaki"
@@ -686,7 +688,8 @@ def main():
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_launch": rows_per_launch * N_TRAIN * 8 + N_TRAIN * N_TRAIN * 8,
                 "peak_source": peak_source,
-                "frac_of_issued_shape_peak": achieved / INT8_PEAK_TOPS_N128 if int8 else None,
+                "mma_shapes": ("M128 K32, N = 64 x stacked W slices: 4 x N256, 2 x N192, 2 x N128, 2 x N64 per k slab "
+                               "(7 x 8-bit scheme)") if int8 else None,
                 "fp64_equiv": {"achieved_tflops": fp64_equiv, "dgemm_peak_tflops": cx.dgemm_peak,
                                "ratio_to_dgemm": fp64_equiv / cx.dgemm_peak,
                                "algorithmic_flops_per_prediction": algo_flops_per_pred},

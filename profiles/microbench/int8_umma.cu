@@ -160,11 +160,45 @@ static void run(int sms) {
     free(h); CK(cudaFree(out));
 }
 
+// The same kernel launched back to back for `seconds`: the rate a long step can sustain under the board's power cap
+// (MEASURED_PEAKS.json distinguishes burst and sustained bf16 the same way); measured over the last 3/4 of the run.
+template <int N, int NSLICE>
+static void run_sustained(int sms, double seconds) {
+    const size_t smem = (size_t)NSLICE * 4096 + (size_t)NSLICE * N * 32 + 1024;
+    CK(cudaFuncSetAttribute(k_umma_probe<N, NSLICE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int* out; CK(cudaMalloc(&out, (size_t)sms * 128 * N * sizeof(int)));
+    const int iters = 2000;
+    cudaEvent_t e0, e1, ew; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&ew));
+    CK(cudaEventRecord(ew));
+    long launches = 0, counted = 0;
+    bool started = false;
+    for (;;) {
+        k_umma_probe<N, NSLICE><<<sms, 128, smem>>>(iters, out, 0);
+        ++launches;
+        if (started) ++counted;
+        if (launches % 16 == 0) {
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            float ms; CK(cudaEventElapsedTime(&ms, ew, e1));
+            if (!started && ms > 250.0 * seconds) { CK(cudaEventRecord(e0)); started = true; }
+            if (ms > 1000.0 * seconds) break;
+        }
+    }
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double macs = (double)sms * iters * NSLICE * NSLICE * 128.0 * N * 32.0 * counted;
+    printf("{\"kernel\": \"tcgen05.mma kind::i8 M128 N%d K32 sustained for %.0f s (back-to-back launches)\", "
+           "\"tops\": %.1f, \"launches\": %ld}\n", N, seconds, 2.0 * macs / (ms * 1e-3) * 1e-12, counted);
+    CK(cudaFree(out));
+}
+
 int main() {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
     const int sms = prop.multiProcessorCount;
     run<64, 8>(sms);
     run<128, 8>(sms);
+    run<192, 6>(sms);
     run<256, 6>(sms);
+    run_sustained<256, 6>(sms, 4.0);
+    run_sustained<128, 8>(sms, 4.0);
     return 0;
 }

@@ -56,7 +56,7 @@ struct bk_gp_s {
     int n = 0, p = 0, P = 0, m = 0, n_pad = 0;
     int var_mode = 0;                // 0 = FP64 DMMA (k_var_trmm), 1 / 2 = int8 tcgen05 (k_var_ozaki, scheme 0 / 1)
     PredictLanes* lanes = nullptr;
-    bool overlap = true;             // bk_gp_set_overlap: K1 of unit u+1 beside the sigma kernel of unit u
+    bool overlap = false;            // bk_gp_set_overlap: K1 of unit u+1 beside the sigma kernel of unit u
     double scale[bk::MAX_P];
     double mn[bk::MAX_P];
     std::vector<bk::GpOutput> out;

@@ -592,18 +592,22 @@ def main():
     host_np = D.cpu().numpy()                                  # pageable, what a caller of SurrogateModel.__call__ holds
     surrogate(host_np[:4096])
 
-    def e2e_time(arr):
+    e2e_runs = {}
+
+    def e2e_time(arr, tag):
+        surrogate(arr)                                          # one untimed full-size call: staging buffers, streams
         times = []
         for _ in range(max(1, min(args.steps, 3))):
             _barrier(cx)
             t0 = time.perf_counter()
             surrogate(arr)
             times.append(time.perf_counter() - t0)
+        e2e_runs[tag] = [round(t, 4) for t in times]
         return _max_over_ranks(cx, float(np.mean(times)))
-    e2e_value = world * e2e_rows / e2e_time(host_np)
+    e2e_value = world * e2e_rows / e2e_time(host_np, 'pageable')
     host_pin = torch.empty((e2e_rows, P_DIM), dtype=torch.float64, pin_memory=True)
     host_pin.copy_(D)
-    e2e_pinned = world * e2e_rows / e2e_time(host_pin.numpy())
+    e2e_pinned = world * e2e_rows / e2e_time(host_pin.numpy(), 'pinned')
     del host_pin
 
     cx.dgemm_peak = measure_dgemm_peak(torch)
@@ -716,7 +720,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(e2e_rows * P_DIM * 8),
                     "d2h_bytes_per_step": int(e2e_rows * 2 * 8),
-                    "api": "SurrogateModel.__call__ (pageable numpy in, numpy out)"},
+                    "api": "SurrogateModel.__call__ (pageable numpy in, numpy out)", "runs_s": e2e_runs.get('pageable')},
             "e2e_pinned": {"value": e2e_pinned, "unit": unit, "note": "same call fed from a pinned host buffer"},
             "gpu_launches": int(var_launches + pred_launches), "roofline": roofline, "roofline_sobol": roofline_sobol,
             "sobol": {"wall_s": sob_wall, "N": args.n_base * world, "rows": args.n_base * world * nb,

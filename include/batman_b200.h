@@ -106,10 +106,12 @@ int bk_gp_set_output_general(bk_gp_t h, int q, int nf, const int* fkind_host, co
 size_t bk_gp_wq_bytes(int n_train);
 int bk_gp_set_output_int8(bk_gp_t h, int q, const int8_t* wq_dev, const double* wsig_dev);
 int bk_gp_set_var_mode(bk_gp_t h, int mode);
-/* A sigma prediction of several units (chunks of points x outputs) runs on two internal streams: K1 of unit u+1
- * (FP64 pipe) beside the sigma kernel of unit u (tensor pipe), on two K* buffers inside the workspace; the caller's
- * stream forks into them and joins again before bk_gp_predict returns.  on = 0 keeps every kernel on the caller's
- * stream, one K* buffer (same results).  Default 1. */
+/* on = 1: a sigma prediction of several units (chunks of points x outputs) runs on two internal streams, K1 of unit
+ * u+1 (FP64 pipe) beside the sigma kernel of unit u (tensor pipe), on two K* buffers inside the workspace; the
+ * caller's stream forks into them and joins again before bk_gp_predict returns.  on = 0 (default): every kernel on the
+ * caller's stream, one K* buffer.  Same results either way.  On a B200 both kernels run into the board's power cap on
+ * their own, so the overlap trades clock for concurrency and the step time does not move (profiles/r02_overlap_probe.jsonl);
+ * the switch exists for boards with power headroom. */
 int bk_gp_set_overlap(bk_gp_t h, int on);
 /* MinMaxScaler of SurrogateModel (surrogate_model.py:108-109,181): x' = x*scale + min.
  * NULL, NULL = identity (Kriging.evaluate receives already-scaled points). */

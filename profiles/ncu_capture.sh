@@ -1,7 +1,7 @@
 #!/bin/bash
 # Run on the GPU box under gpurun: launch list + one full capture per hot kernel, exported as CSV
 # (the .ncu-rep files with imported source exceed gpurun's 64 MiB return limit, so only CSV pages come back).
-CMD="python bench.py --steps 2 --warmup 1 --n-base 50000 --no-cpu-baseline"
+CMD="python bench.py --steps 2 --warmup 1 --n-base 50000 --no-cpu-baseline --no-configs"
 OUT=gpurun_out
 $CMD > $OUT/plain.log 2>&1 || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1

@@ -293,3 +293,64 @@ def test_c_abi_predict_stays_inside_its_buffers():
         got_s = std[pad:pad + k * m].reshape(k, m).cpu().numpy()
         om, osd = ogp.evaluate(states, pts.cpu().numpy())
         _check(got_m, got_s, om, osd, states)
+
+
+def test_overlap_lanes_give_identical_results():
+    """bk_gp_set_overlap(1): K1 of unit u+1 beside the sigma kernel of unit u on two internal streams and two K*
+    buffers -- same bits as the single-stream path, for several chunks (small workspace) x two outputs, both sigma
+    kernels, called twice in a row on the caller's stream (the fork/join must order consecutive calls)."""
+    import ctypes
+    import torch
+    from batman_b200 import _lib
+    from oracle import functions as ofun
+    lib = _lib.load()
+    p, n = 4, 300
+    X = ofun.halton(n, p)
+    ls = np.full(p, 0.6)
+    states = [ogp.fit_state(('prod', ('const', 1.3), ('matern', 1.5, ls)), X, ofun.g_function(X)[:, 0]),
+              ogp.fit_state(('prod', ('const', 0.8), ('matern', 2.5, 1.5 * ls)), X, np.sin(4 * X[:, 0]) + X[:, 1])]
+    model = kriging_from_states(states)._model()
+    model.ensure_w()
+    k = 3000
+    pts = torch.rand((k, p), dtype=torch.float64, device='cuda')
+    per_point = model.n_pad * 8
+    ws_bytes = 2 * 1024 * per_point + 256                   # two K* buffers of 1024 points: 3 chunks x 2 outputs = 6 units
+    ws = torch.zeros(ws_bytes // 8 + 1, dtype=torch.float64, device='cuda')
+    for kernel in ('int8', 'dmma'):
+        model.set_sigma_kernel(kernel)
+        res = []
+        for on in (0, 1, 1):
+            _lib.check(lib.bk_gp_set_overlap(model.handle, on))
+            mean = torch.zeros((k, 2), dtype=torch.float64, device='cuda')
+            std = torch.zeros((k, 2), dtype=torch.float64, device='cuda')
+            _lib.check(lib.bk_gp_predict(model.handle, ctypes.c_void_p(pts.data_ptr()), k, ctypes.c_void_p(mean.data_ptr()),
+                                         ctypes.c_void_p(std.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws_bytes, None))
+            fault = ctypes.c_int(-1)
+            _lib.check(lib.bk_gp_predict_status(ctypes.c_void_p(ws.data_ptr()), ws_bytes, ctypes.byref(fault), None))
+            assert fault.value == 0
+            res.append((mean.cpu().numpy(), std.cpu().numpy()))
+        _lib.check(lib.bk_gp_set_overlap(model.handle, 0))
+        for m_on, s_on in res[1:]:
+            assert np.array_equal(res[0][0], m_on) and np.array_equal(res[0][1], s_on)
+        om, osd = ogp.evaluate(states, pts.cpu().numpy())
+        _check(res[1][0], res[1][1], om, osd, states)
+
+
+def test_pipelined_host_path_matches_single_call():
+    """DeviceModel.predict above E2E_CHUNK rows (pinned staging buffers filled and emptied by helper threads, three
+    streams): same bits as one resident call, ragged last slice, with and without sigma."""
+    import torch
+    from batman_b200.device_model import DeviceModel
+    from oracle import functions as ofun
+    p, n = 3, 128
+    X = ofun.halton(n, p)
+    states = [ogp.fit_state(('prod', ('const', 1.1), ('matern', 1.5, np.full(p, 0.5))), X, ofun.g_function(X)[:, 0])]
+    model = kriging_from_states(states)._model()
+    k = 2 * DeviceModel.E2E_CHUNK + 12345
+    rng = np.random.RandomState(3)
+    pts = rng.rand(k, p)
+    mean, std = model.predict(pts, return_std=True)
+    dm, ds = model.predict_device(torch.from_numpy(pts).cuda(), return_std=True)
+    assert np.array_equal(mean, dm.cpu().numpy()) and np.array_equal(std, ds.cpu().numpy())
+    mean2, none = model.predict(pts, return_std=False)
+    assert none is None and np.array_equal(mean2, mean)

@@ -207,23 +207,154 @@ __global__ void __launch_bounds__(256) k_zdot(const double* __restrict__ M, long
 }
 
 // ---------------------------------------------------------------- diagonal block: factor, invert, forward-solve
+// One CTA per candidate works on the 128 x 128 diagonal block in shared memory, blocked by 32 so that the serial
+// part (a 32 x 32 factorisation / inversion in the registers of ONE warp, shuffles instead of block barriers) is short
+// and everything else is a small matrix product over all 256 threads.  The Cholesky performs, element by element,
+// the same operations in the same order as the unblocked right-looking algorithm (scale by the reciprocal pivot,
+// rank-1 updates in column order), so its results do not depend on the blocking.
 constexpr int DP = NB + 1;   // shared pitch
-constexpr size_t DIAG_SMEM = ((size_t)NB * DP + 2 * NB) * 8;
+constexpr int DB = 32;       // inner block
+constexpr size_t DIAG_SMEM = ((size_t)NB * DP + 3 * NB + DB * (DB + 1)) * 8;
 
-// in-place inverse of the lower-triangular matrix held in a[NB][DP] (column sweep from the right, as LAPACK dtrti2)
-__device__ void tri_invert_smem(double* a) {
-    const int tid = threadIdx.x;
-    for (int j = NB - 1; j >= 0; --j) {
-        __syncthreads();
-        const double ajj = 1.0 / a[j * DP + j];
+// Cholesky of the 32 x 32 diagonal block at (j0, j0) by one warp: lane = row, the row lives in registers.
+// Writes L (zeros above the diagonal) back, the reciprocal pivots to rinv[j0 ..], returns the first non-positive
+// pivot (1-based, local) or 0.
+__device__ __forceinline__ int chol32_warp(double* a, int j0, int lane, double* rinv) {
+    double r[DB];
+#pragma unroll
+    for (int c = 0; c < DB; ++c) r[c] = a[(j0 + lane) * DP + j0 + c];       // the strict upper triangle of a is zero
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < DB; ++j) {
+        const double d = __shfl_sync(0xffffffffu, r[j], j);
+        if (!(d > 0.0) && bad == 0) bad = j + 1;
+        const double piv = sqrt(d), inv = 1.0 / piv;
+        const double lj = lane > j ? r[j] * inv : (lane == j ? piv : r[j]);
+        r[j] = lj;
+        if (lane == j) rinv[j0 + j] = inv;
+#pragma unroll
+        for (int c = j + 1; c < DB; ++c) {
+            const double lc = __shfl_sync(0xffffffffu, lj, c);
+            r[c] = lane >= c ? fma(-lj, lc, r[c]) : r[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < DB; ++c) a[(j0 + lane) * DP + j0 + c] = c <= lane ? r[c] : 0.0;
+    return bad;
+}
+
+// Inverse of the lower-triangular 32 x 32 block at (j0, j0) by one warp: lane = column k, forward substitution of
+// L x = e_k with x in registers; L entries are shared-memory broadcasts.  out[i][k], pitch DB + 1.
+__device__ __forceinline__ void inv32_warp(const double* a, int j0, int lane, double* out) {
+    double x[DB];
+#pragma unroll
+    for (int i = 0; i < DB; ++i) {
+        const double rd = 1.0 / a[(j0 + i) * DP + j0 + i];
         double sum = 0.0;
-        const int i = tid;
-        if (i > j && i < NB) {
-            for (int cidx = j + 1; cidx <= i; ++cidx) sum = fma(a[i * DP + cidx], a[cidx * DP + j], sum);
+#pragma unroll
+        for (int c = 0; c < i; ++c) sum = fma(a[(j0 + i) * DP + j0 + c], x[c], sum);     // x[c] = 0 for c < k
+        x[i] = i < lane ? 0.0 : (i == lane ? rd : -sum * rd);
+        out[i * (DB + 1) + lane] = x[i];
+    }
+}
+
+// blocked Cholesky of a[NB][DP] (lower), 4 panels of 32 columns; returns through bad_s the first bad pivot (1-based)
+__device__ void chol_block_smem(double* a, double* rinv, double* scratch, int* bad_s) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j0 = 0; j0 < NB; j0 += DB) {
+        const int m = NB - DB - j0;                  // rows below the diagonal block
+        __syncthreads();
+        if (warp == 0) {
+            const int b = chol32_warp(a, j0, lane, rinv);
+            if (lane == 0 && b != 0 && *bad_s == 0) *bad_s = j0 + b;
         }
         __syncthreads();
-        if (i > j && i < NB) a[i * DP + j] = -sum * ajj;
-        if (tid == j) a[j * DP + j] = ajj;
+        if (tid < m) {
+            // panel rows: x = a[i, panel] L11^-T by substitution, the order of the unblocked algorithm
+            const int i = j0 + DB + tid;
+            double x[DB];
+#pragma unroll
+            for (int c = 0; c < DB; ++c) x[c] = a[i * DP + j0 + c];
+#pragma unroll
+            for (int t = 0; t < DB; ++t) {
+                x[t] *= rinv[j0 + t];
+#pragma unroll
+                for (int c = t + 1; c < DB; ++c) x[c] = fma(-x[t], a[(j0 + c) * DP + j0 + t], x[c]);
+            }
+#pragma unroll
+            for (int c = 0; c < DB; ++c) a[i * DP + j0 + c] = x[c];
+        }
+        __syncthreads();
+        // trailing update (lower triangle): a[i][c] -= sum_t x[i][t] x[c][t], t ascending.  lane = column inside a
+        // 32-wide column block, a warp walks rows: x[i][.] is a broadcast, x[c][.] is conflict free (pitch 129).
+        const int r0 = j0 + DB;
+        for (int cb = 0; cb < m; cb += DB) {
+            const int c = r0 + cb + lane;
+            for (int i = r0 + cb + warp; i < NB; i += 8) {
+                if (c <= i) {
+                    double acc = a[i * DP + c];
+#pragma unroll 8
+                    for (int t = 0; t < DB; ++t) acc = fma(-a[i * DP + j0 + t], a[c * DP + j0 + t], acc);
+                    a[i * DP + c] = acc;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    (void)scratch;
+}
+
+// in-place inverse of the lower-triangular matrix in a[NB][DP], block columns from the right (LAPACK dtrtri):
+//   W21 = -W22 L21 L11^-1,  W11 = L11^-1   with W22 the already inverted trailing block
+__device__ void tri_invert_smem(double* a, double* dsc /* [DB][DB+1] */) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j0 = NB - DB; j0 >= 0; j0 -= DB) {
+        const int m = NB - DB - j0, r0 = j0 + DB;
+        __syncthreads();
+        if (warp == 0) inv32_warp(a, j0, lane, dsc);
+        double acc[(NB - DB) / 8];
+        if (m > 0) {
+            // T = W22 L21: thread = (column lane, rows warp + 8 k)
+#pragma unroll
+            for (int kk = 0; kk < (NB - DB) / 8; ++kk) acc[kk] = 0.0;
+            for (int t = 0; t < m; ++t) {
+                const double l = a[(r0 + t) * DP + j0 + lane];
+#pragma unroll
+                for (int kk = 0; kk < (NB - DB) / 8; ++kk) {
+                    const int r = warp + 8 * kk;
+                    if (r < m && r >= t) acc[kk] = fma(a[(r0 + r) * DP + r0 + t], l, acc[kk]);
+                }
+            }
+        }
+        __syncthreads();                       // every read of L21 and W22 done; inv32 finished
+        if (m > 0) {
+#pragma unroll
+            for (int kk = 0; kk < (NB - DB) / 8; ++kk) {
+                const int r = warp + 8 * kk;
+                if (r < m) a[(r0 + r) * DP + j0 + lane] = acc[kk];
+            }
+        }
+        __syncthreads();
+        if (m > 0) {
+            // W21 = -T L11^-1: out[r][c] = -sum_{t >= c} T[r][t] Dinv[t][c]
+#pragma unroll
+            for (int kk = 0; kk < (NB - DB) / 8; ++kk) {
+                const int r = warp + 8 * kk;
+                double sum = 0.0;
+                if (r < m)
+                    for (int t = 0; t < DB; ++t) sum = fma(a[(r0 + r) * DP + j0 + t], dsc[t * (DB + 1) + lane], sum);   // Dinv[t][c] = 0 for t < c
+                acc[kk] = -sum;
+            }
+        }
+        __syncthreads();
+        if (m > 0) {
+#pragma unroll
+            for (int kk = 0; kk < (NB - DB) / 8; ++kk) {
+                const int r = warp + 8 * kk;
+                if (r < m) a[(r0 + r) * DP + j0 + lane] = acc[kk];
+            }
+        }
+        for (int e = tid; e < DB * DB; e += 256) a[(j0 + (e >> 5)) * DP + j0 + (e & 31)] = dsc[(e >> 5) * (DB + 1) + (e & 31)];
     }
     __syncthreads();
 }
@@ -240,10 +371,14 @@ k_diag_block(double* __restrict__ M, long m_batch, int ld, int k, double* __rest
     double* a = sm;                  // [NB][DP]
     double* sv = sm + NB * DP;       // [NB] rhs of the forward solve
     double* zk = sv + NB;            // [NB]
+    double* rinv = zk + NB;          // [NB] reciprocal pivots
+    double* dsc = rinv + NB;         // [DB][DB+1] inverse of the current 32 x 32 diagonal block
+    __shared__ int bad_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = blockIdx.x;
     double* Mr = M + (size_t)r * m_batch;
     double* blk = Mr + (size_t)k * NB * ld + (size_t)k * NB;
+    if (tid == 0) bad_s = 0;
     for (int idx = tid; idx < NB * NB; idx += 256) {
         const int i = idx >> 7, cidx = idx & 127;
         double v = cidx <= i ? blk[(size_t)i * ld + cidx] : 0.0;
@@ -253,25 +388,8 @@ k_diag_block(double* __restrict__ M, long m_batch, int ld, int k, double* __rest
     }
     if constexpr (FACTOR) {
         if (tid < NB) sv[tid] = sv_in[(size_t)r * NB + tid];       // s = y_k - L[k, <k] z_<k (k_zdot)
-        // unblocked right-looking Cholesky in shared memory
-        int bad = 0;
-        for (int j = 0; j < NB; ++j) {
-            __syncthreads();
-            const double d = a[j * DP + j];
-            if (!(d > 0.0) && bad == 0) bad = k * NB + j + 1;       // not positive definite (sklearn:_gpr.py:591-593)
-            const double piv = sqrt(d), inv = 1.0 / piv;
-            __syncthreads();
-            if (tid == j) a[j * DP + j] = piv;
-            if (tid > j && tid < NB) a[tid * DP + j] *= inv;
-            __syncthreads();
-            const int ti = tid >> 4, tc = tid & 15;
-            for (int i = j + 1 + ti; i < NB; i += 16) {
-                const double li = a[i * DP + j];
-                for (int cidx = j + 1 + tc; cidx <= i; cidx += 16) a[i * DP + cidx] = fma(-li, a[cidx * DP + j], a[i * DP + cidx]);
-            }
-        }
-        __syncthreads();
-        if (tid == 0 && bad != 0 && info[r] == 0) info[r] = bad;
+        chol_block_smem(a, rinv, dsc, &bad_s);
+        if (tid == 0 && bad_s != 0 && info[r] == 0) info[r] = k * NB + bad_s;   // not positive definite (sklearn:_gpr.py:591-593)
         for (int idx = tid; idx < NB * NB; idx += 256) {
             const int i = idx >> 7, cidx = idx & 127;
             blk[(size_t)i * ld + cidx] = a[i * DP + cidx];          // L_kk (upper part zero)
@@ -288,7 +406,7 @@ k_diag_block(double* __restrict__ M, long m_batch, int ld, int k, double* __rest
             acc[2 * r] += t;
         }
     }
-    tri_invert_smem(a);
+    tri_invert_smem(a, dsc);
     double* Wr = Winv + (size_t)r * w_batch + (size_t)k * NB * NB;
     for (int idx = tid; idx < NB * NB; idx += 256) {
         const int i = idx >> 7, cidx = idx & 127;
@@ -423,86 +541,132 @@ static int general_cands(std::vector<Cand>& h, int R, int p, int nf, const int* 
 
 // Side stream (highest priority) for the latency-bound single-CTA diagonal-block kernel: it runs while the main
 // stream updates the block rows below the diagonal (look-ahead), so only the row-k update sits on the critical path.
+// Streams of the factorisation.  The diagonal-block kernel (one latency-bound CTA per candidate, 140 KiB of shared
+// memory, 146 registers) cannot share an SM with the 200-register GEMM CTAs, so with >= 64 candidates the batch is
+// split into two groups that walk the block columns half a step apart, each on its own (main, side) stream pair:
+// while one group's diagonal blocks occupy half of the SMs, the other group's GEMMs fill the rest.
 struct SideStream {
-    cudaStream_t s = nullptr;
-    cudaEvent_t e_main = nullptr, e_side = nullptr;
+    cudaStream_t s = nullptr;        // diagonal block + forward-solve step (high priority)
+    cudaStream_t main2 = nullptr;    // main stream of the second candidate group
+    cudaEvent_t e_main = nullptr, e_side = nullptr, e_fork = nullptr, e_join = nullptr;
 };
-static int side_stream(SideStream** out) {
-    static SideStream per_dev[64];
+static int side_streams(SideStream** out) {
+    static SideStream per_dev[64][2];
     int dev = 0;
     BK_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return set_error("device ordinal %d out of range", dev);
-    SideStream& ss = per_dev[dev];
-    if (!ss.s) {
-        int lo = 0, hi = 0;
-        BK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        BK_CUDA(cudaStreamCreateWithPriority(&ss.s, cudaStreamNonBlocking, hi));
-        BK_CUDA(cudaEventCreateWithFlags(&ss.e_main, cudaEventDisableTiming));
-        BK_CUDA(cudaEventCreateWithFlags(&ss.e_side, cudaEventDisableTiming));
+    for (int g = 0; g < 2; ++g) {
+        SideStream& ss = per_dev[dev][g];
+        if (!ss.s) {
+            int lo = 0, hi = 0;
+            BK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            BK_CUDA(cudaStreamCreateWithPriority(&ss.s, cudaStreamNonBlocking, hi));
+            BK_CUDA(cudaStreamCreateWithFlags(&ss.main2, cudaStreamNonBlocking));
+            BK_CUDA(cudaEventCreateWithFlags(&ss.e_main, cudaEventDisableTiming));
+            BK_CUDA(cudaEventCreateWithFlags(&ss.e_side, cudaEventDisableTiming));
+            BK_CUDA(cudaEventCreateWithFlags(&ss.e_fork, cudaEventDisableTiming));
+            BK_CUDA(cudaEventCreateWithFlags(&ss.e_join, cudaEventDisableTiming));
+        }
     }
-    *out = &ss;
+    *out = per_dev[dev];
     return 0;
 }
 
-// blocked Cholesky of the R matrices in w.M (in place), z and the accumulators alongside
-static int cholesky_sweep(const LmlWorkspace& w, int n, int R, double* WT, cudaStream_t st) {
+// candidates [r0, r0 + R) of a workspace as a workspace of their own
+static LmlWorkspace group_view(const LmlWorkspace& w, int n, int r0) {
+    const size_t n_pad = padded_n(n), nP = n_pad / NB;
+    LmlWorkspace v = w;
+    v.cands = w.cands + r0;
+    v.M = w.M + (size_t)r0 * n_pad * n_pad;
+    v.Winv = w.Winv + (size_t)r0 * nP * NB * NB;
+    v.z = w.z + (size_t)r0 * n_pad;
+    v.acc = w.acc + 2 * (size_t)r0;
+    v.info = w.info + r0;
+    v.sv = w.sv + (size_t)r0 * NB;
+    v.part = w.part + (size_t)r0 * SPLIT_MAX * NB * NB;
+    return v;                        // ypad is indexed by the candidate's absolute target row
+}
+
+// block column k of the Cholesky of the R matrices in w.M (in place), z and the accumulators alongside
+static int cholesky_column(const LmlWorkspace& w, int n, int R, int k, double* WT, cudaStream_t st, SideStream* ss) {
     const int n_pad = padded_n(n), nP = n_pad / NB;
     const long mb = (long)n_pad * n_pad, wb = (long)nP * NB * NB;
+    int nsplit = 0;
+    if (k > 0) {
+        // the diagonal block first, split-K over up to SPLIT_MAX CTAs per candidate: partial products go to
+        // scratch and are subtracted by the diagonal-block kernel when it loads T_kk
+        const int per = (k + SPLIT_MAX - 1) / SPLIT_MAX;               // 128-column blocks per slice
+        nsplit = (k + per - 1) / per;
+        GemmArgs g;
+        g.A = w.M + (size_t)k * NB * n_pad; g.a_batch = mb; g.a_tile = (long)per * NB; g.lda = n_pad;
+        g.B = g.A; g.b_batch = mb; g.b_tile = (long)per * NB; g.ldb = n_pad;
+        g.C = w.part; g.c_batch = (long)SPLIT_MAX * NB * NB; g.c_tile = (long)NB * NB; g.ldc = NB;
+        g.K0 = per * NB; g.k_tile = 0; g.alpha = 1.0; g.beta = 0.0; g.split_k_total = k * NB;
+        if (int rc = gemm_nt(g, nsplit, R, st)) return rc;
+    }
+    BK_CUDA(cudaEventRecord(ss->e_main, st));
+    BK_CUDA(cudaStreamWaitEvent(ss->s, ss->e_main, 0));
+    {
+        ProfScope prof(PROF_CHOL, ss->s);
+        k_zdot<<<dim3(R, NB / 8), 256, 0, ss->s>>>(w.M, mb, n_pad, k, w.cands, w.ypad, w.z, n_pad, w.sv);
+        BK_LAUNCH_CHECK("k_zdot");
+        k_diag_block<true><<<R, 256, DIAG_SMEM, ss->s>>>(w.M, mb, n_pad, k, w.Winv, wb, WT, mb, w.sv, w.z, n_pad, w.acc, w.info,
+                                                         w.part, nsplit);
+        BK_LAUNCH_CHECK("k_diag_block<true>");
+    }
+    BK_CUDA(cudaEventRecord(ss->e_side, ss->s));
+    if (k > 0 && k + 1 < nP) {
+        // T_ik = A_ik - L[i, <k] L[k, <k]^T for the block rows below the diagonal: overlaps the diagonal block
+        GemmArgs g;
+        g.A = w.M + (size_t)(k + 1) * NB * n_pad; g.a_batch = mb; g.a_tile = (long)NB * n_pad; g.lda = n_pad;
+        g.B = w.M + (size_t)k * NB * n_pad; g.b_batch = mb; g.b_tile = 0; g.ldb = n_pad;
+        g.C = w.M + (size_t)(k + 1) * NB * n_pad + (size_t)k * NB; g.c_batch = mb; g.c_tile = (long)NB * n_pad; g.ldc = n_pad;
+        g.K0 = k * NB; g.k_tile = 0; g.alpha = -1.0; g.beta = 1.0;
+        if (int rc = gemm_nt(g, nP - k - 1, R, st)) return rc;
+    }
+    BK_CUDA(cudaStreamWaitEvent(st, ss->e_side, 0));
+    if (k + 1 < nP) {   // L_ik = T_ik Winv_k^T, i = k+1..nP-1 (in place)
+        GemmArgs g;
+        g.A = w.M + (size_t)(k + 1) * NB * n_pad + (size_t)k * NB; g.a_batch = mb; g.a_tile = (long)NB * n_pad; g.lda = n_pad;
+        g.B = w.Winv + (size_t)k * NB * NB; g.b_batch = wb; g.b_tile = 0; g.ldb = NB;
+        g.C = const_cast<double*>(g.A); g.c_batch = mb; g.c_tile = (long)NB * n_pad; g.ldc = n_pad;
+        g.K0 = NB; g.k_tile = 0; g.alpha = 1.0; g.beta = 0.0;
+        if (int rc = gemm_nt(g, nP - k - 1, R, st)) return rc;
+    }
+    return 0;
+}
+
+// blocked Cholesky of the R matrices in w.M (in place)
+static int cholesky_sweep(const LmlWorkspace& w, int n, int R, double* WT, cudaStream_t st) {
+    const int nP = padded_n(n) / NB;
     static OncePerDevice attr;
     if (attr.first()) {
         BK_CUDA(cudaFuncSetAttribute(k_diag_block<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
         BK_CUDA(cudaFuncSetAttribute(k_diag_block<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DIAG_SMEM));
     }
     SideStream* ss = nullptr;
-    if (int rc = side_stream(&ss)) return rc;
+    if (int rc = side_streams(&ss)) return rc;
     BK_CUDA(cudaMemsetAsync(w.acc, 0, sizeof(double) * 2 * R, st));
     BK_CUDA(cudaMemsetAsync(w.info, 0, sizeof(int) * R, st));
-    // T_ik = A_ik - L[i, <k] L[k, <k]^T for the block rows i = i0 .. i0 + tiles - 1
-    auto update = [&](int k, int i0, int tiles) {
-        GemmArgs g;
-        g.A = w.M + (size_t)i0 * NB * n_pad; g.a_batch = mb; g.a_tile = (long)NB * n_pad; g.lda = n_pad;
-        g.B = w.M + (size_t)k * NB * n_pad; g.b_batch = mb; g.b_tile = 0; g.ldb = n_pad;
-        g.C = w.M + (size_t)i0 * NB * n_pad + (size_t)k * NB; g.c_batch = mb; g.c_tile = (long)NB * n_pad; g.ldc = n_pad;
-        g.K0 = k * NB; g.k_tile = 0; g.alpha = -1.0; g.beta = 1.0;
-        return gemm_nt(g, tiles, R, st);
-    };
-    for (int k = 0; k < nP; ++k) {
-        int nsplit = 0;
-        if (k > 0) {
-            // the diagonal block first, split-K over up to SPLIT_MAX CTAs per candidate: partial products go to
-            // scratch and are subtracted by the diagonal-block kernel when it loads T_kk
-            const int per = (k + SPLIT_MAX - 1) / SPLIT_MAX;               // 128-column blocks per slice
-            nsplit = (k + per - 1) / per;
-            GemmArgs g;
-            g.A = w.M + (size_t)k * NB * n_pad; g.a_batch = mb; g.a_tile = (long)per * NB; g.lda = n_pad;
-            g.B = g.A; g.b_batch = mb; g.b_tile = (long)per * NB; g.ldb = n_pad;
-            g.C = w.part; g.c_batch = (long)SPLIT_MAX * NB * NB; g.c_tile = (long)NB * NB; g.ldc = NB;
-            g.K0 = per * NB; g.k_tile = 0; g.alpha = 1.0; g.beta = 0.0; g.split_k_total = k * NB;
-            if (int rc = gemm_nt(g, nsplit, R, st)) return rc;
-        }
-        BK_CUDA(cudaEventRecord(ss->e_main, st));
-        BK_CUDA(cudaStreamWaitEvent(ss->s, ss->e_main, 0));
-        {
-            ProfScope prof(PROF_CHOL, ss->s);
-            k_zdot<<<dim3(R, NB / 8), 256, 0, ss->s>>>(w.M, mb, n_pad, k, w.cands, w.ypad, w.z, n_pad, w.sv);
-            BK_LAUNCH_CHECK("k_zdot");
-            k_diag_block<true><<<R, 256, DIAG_SMEM, ss->s>>>(w.M, mb, n_pad, k, w.Winv, wb, WT, mb, w.sv, w.z, n_pad, w.acc, w.info,
-                                                             w.part, nsplit);
-            BK_LAUNCH_CHECK("k_diag_block<true>");
-        }
-        BK_CUDA(cudaEventRecord(ss->e_side, ss->s));
-        if (k > 0 && k + 1 < nP)
-            if (int rc = update(k, k + 1, nP - k - 1)) return rc;          // rows below: overlaps the diagonal block
-        BK_CUDA(cudaStreamWaitEvent(st, ss->e_side, 0));
-        if (k + 1 < nP) {   // L_ik = T_ik Winv_k^T, i = k+1..nP-1 (in place)
-            GemmArgs g;
-            g.A = w.M + (size_t)(k + 1) * NB * n_pad + (size_t)k * NB; g.a_batch = mb; g.a_tile = (long)NB * n_pad; g.lda = n_pad;
-            g.B = w.Winv + (size_t)k * NB * NB; g.b_batch = wb; g.b_tile = 0; g.ldb = NB;
-            g.C = const_cast<double*>(g.A); g.c_batch = mb; g.c_tile = (long)NB * n_pad; g.ldc = n_pad;
-            g.K0 = NB; g.k_tile = 0; g.alpha = 1.0; g.beta = 0.0;
-            if (int rc = gemm_nt(g, nP - k - 1, R, st)) return rc;
-        }
+    if (R < 64 || WT != nullptr) {
+        for (int k = 0; k < nP; ++k)
+            if (int rc = cholesky_column(w, n, R, k, WT, st, &ss[0])) return rc;
+        return 0;
     }
+    const int R0 = (R + 1) / 2;
+    const LmlWorkspace w1 = group_view(w, n, R0);
+    cudaStream_t st1 = ss[1].main2;
+    BK_CUDA(cudaEventRecord(ss[1].e_fork, st));
+    BK_CUDA(cudaStreamWaitEvent(st1, ss[1].e_fork, 0));
+    for (int k = 0; k < nP; ++k) {
+        if (int rc = cholesky_column(w, n, R0, k, nullptr, st, &ss[0])) return rc;
+        // stagger: the second group starts when the first group's first diagonal block is done, so that from then on
+        // one group's diagonal blocks run beside the other group's GEMMs instead of beside its own twin
+        if (k == 0) BK_CUDA(cudaStreamWaitEvent(st1, ss[0].e_side, 0));
+        if (int rc = cholesky_column(w1, n, R - R0, k, nullptr, st1, &ss[1])) return rc;
+    }
+    BK_CUDA(cudaEventRecord(ss[1].e_join, st1));
+    BK_CUDA(cudaStreamWaitEvent(st, ss[1].e_join, 0));
     return 0;
 }
 

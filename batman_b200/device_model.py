@@ -191,28 +191,16 @@ class DeviceModel:
                 self.check_pipeline_flag()
         return mean, std
 
-    E2E_CHUNK = 4 * 148 * 128 * 8     # rows per pipelined host slice (four K* chunks of 151 552 rows)
-
-    def _staging(self, return_std):
-        """Two pinned input and two pinned output slices (allocated once per model): the caller's pageable arrays are
-        copied through them by helper threads, so every host<->device transfer is asynchronous."""
-        st = getattr(self, '_stage', None)
-        if st is None:
-            st = {'in': [torch.empty((self.E2E_CHUNK, self.p), dtype=torch.float64).pin_memory() for _ in range(2)],
-                  'mean': [torch.empty((self.E2E_CHUNK, self.m), dtype=torch.float64).pin_memory() for _ in range(2)],
-                  'std': None}
-            self._stage = st
-        if return_std and st['std'] is None:
-            st['std'] = [torch.empty((self.E2E_CHUNK, self.m), dtype=torch.float64).pin_memory() for _ in range(2)]
-        return st
+    E2E_CHUNK = 2 * 148 * 128 * 8     # rows per pipelined host slice (two K* chunks of 151 552 rows)
 
     def predict(self, points, return_std=True):
         """numpy in, numpy out (the Kriging.evaluate boundary): host<->device copies included.
 
-        Large batches are pipelined over slices of E2E_CHUNK rows.  A helper thread copies slice c+1 of the caller's
-        (pageable) array into a pinned staging buffer while the GPU predicts slice c; the upload, the kernels and the
-        download of consecutive slices run on three streams; a second helper thread moves finished results from the
-        pinned output buffer into the returned arrays.  The GPU never waits for a pageable copy."""
+        Large batches are pipelined: while slice c is being predicted, slice c+1 is uploaded on a copy stream
+        and the results of slice c-1 are downloaded on another (the download blocks the host thread only, the
+        GPU already has the next slice's kernels queued).  Pageable arrays are handed to the driver as they are: its
+        staged copies (10-20 GB/s) were steadier than a pinned staging ring filled by helper threads, alone and with
+        4 ranks on one host (profiles/r02_e2e_probe*.jsonl)."""
         points = np.ascontiguousarray(points, dtype=np.float64)
         k = points.shape[0]
         src = torch.from_numpy(points)
@@ -221,62 +209,37 @@ class DeviceModel:
                 pts = src.to(self.device, non_blocking=False)
                 mean, std = self.predict_device(pts, return_std)
                 return mean.cpu().numpy(), (std.cpu().numpy() if std is not None else None)
-            from concurrent.futures import ThreadPoolExecutor
             out_mean = np.empty((k, self.m))
             out_std = np.empty((k, self.m)) if return_std else None
-            dst_mean = torch.from_numpy(out_mean)
-            dst_std = torch.from_numpy(out_std) if return_std else None
-            stage = self._staging(return_std)
             s_main = torch.cuda.current_stream()
             s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
             bounds = [(lo, min(lo + self.E2E_CHUNK, k)) for lo in range(0, k, self.E2E_CHUNK)]
-            n_sl = len(bounds)
-            up_done = [None] * n_sl          # events: upload of slice c has left its pinned buffer
-            down_done = [None] * n_sl        # events: results of slice c are in their pinned buffer
-            out_futs = [None] * n_sl
-
-            def stage_in(c):
-                lo, hi = bounds[c]
-                if c >= 2:
-                    up_done[c - 2].synchronize()         # buffer c & 1 was last uploaded for slice c - 2
-                stage['in'][c & 1][:hi - lo].copy_(src[lo:hi])
-
-            def stage_out(c):
-                lo, hi = bounds[c]
-                down_done[c].synchronize()
-                dst_mean[lo:hi].copy_(stage['mean'][c & 1][:hi - lo])
-                if return_std:
-                    dst_std[lo:hi].copy_(stage['std'][c & 1][:hi - lo])
-
-            with ThreadPoolExecutor(1) as pool_in, ThreadPoolExecutor(1) as pool_out:
-                fut_in = pool_in.submit(stage_in, 0)
-                for c, (lo, hi) in enumerate(bounds):
-                    fut_in.result()
+            pending = None
+            for c in range(len(bounds) + 1):
+                if c < len(bounds):
+                    lo, hi = bounds[c]
                     with torch.cuda.stream(s_in):
-                        pts = stage['in'][c & 1][:hi - lo].to(self.device, non_blocking=True)
-                        up_done[c] = torch.cuda.Event()
-                        up_done[c].record(s_in)
-                    if c + 1 < n_sl:
-                        fut_in = pool_in.submit(stage_in, c + 1)
-                    s_main.wait_event(up_done[c])
+                        pts = src[lo:hi].to(self.device, non_blocking=True)
+                        ev_in = torch.cuda.Event()
+                        ev_in.record(s_in)
+                    s_main.wait_event(ev_in)
                     pts.record_stream(s_main)
                     mean, std = self.predict_device(pts, return_std, check=False)
                     ev = torch.cuda.Event()
                     ev.record(s_main)
-                    if c >= 2:
-                        out_futs[c - 2].result()         # output buffer c & 1 has been emptied
+                    nxt = (lo, hi, mean, std, ev)
+                else:
+                    nxt = None
+                if pending is not None:
+                    plo, phi, pmean, pstd, pev = pending
                     with torch.cuda.stream(s_out):
-                        s_out.wait_event(ev)
-                        mean.record_stream(s_out)
-                        stage['mean'][c & 1][:hi - lo].copy_(mean, non_blocking=True)
-                        if std is not None:
-                            std.record_stream(s_out)
-                            stage['std'][c & 1][:hi - lo].copy_(std, non_blocking=True)
-                        down_done[c] = torch.cuda.Event()
-                        down_done[c].record(s_out)
-                    out_futs[c] = pool_out.submit(stage_out, c)
-                for f in out_futs:
-                    f.result()
+                        s_out.wait_event(pev)
+                        pmean.record_stream(s_out)
+                        torch.from_numpy(out_mean[plo:phi]).copy_(pmean)
+                        if pstd is not None:
+                            pstd.record_stream(s_out)
+                            torch.from_numpy(out_std[plo:phi]).copy_(pstd)
+                pending = nxt
             s_main.synchronize()
             if return_std:
                 self.check_pipeline_flag()

@@ -337,8 +337,8 @@ def test_overlap_lanes_give_identical_results():
 
 
 def test_pipelined_host_path_matches_single_call():
-    """DeviceModel.predict above E2E_CHUNK rows (pinned staging buffers filled and emptied by helper threads, three
-    streams): same bits as one resident call, ragged last slice, with and without sigma."""
+    """DeviceModel.predict above E2E_CHUNK rows (slices uploaded, predicted and downloaded on three streams): same
+    bits as one resident call, ragged last slice, with and without sigma."""
     import torch
     from batman_b200.device_model import DeviceModel
     from oracle import functions as ofun

@@ -44,7 +44,7 @@ ProfScope::~ProfScope() {
 int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* mean, double* kstar, int8_t* kq,
                    int kq_scheme, double kappa, cudaStream_t st);
 int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, double kappa, long k, double* std_out,
-                     int* fail_flag, cudaStream_t st);
+                     double* scratch, int* fail_flag, cudaStream_t st);
 int launch_var(const bk_gp_s* h, int q, const double* kstar, long k, double* std_out, cudaStream_t st);
 int launch_pack_w(const double* w, int n, double* out, cudaStream_t st);
 int launch_sobol(const bk_gp_s* h, int q, const double* a, const double* b, uint64_t seed, const int* mkind,
@@ -256,8 +256,9 @@ static double pow2_at_least(double v) {
     return ldexp(1.0, e);
 }
 
-// per point: K* tile bytes (FP64 fragments or 8 int8 slices: both n_pad * 8)
-static size_t predict_bytes_per_point(const bk_gp_s* h) { return (size_t)h->n_pad * sizeof(double); }
+// per point: K* tile bytes (FP64 fragments or 8 int8 slices: both n_pad * 8) + 24 bytes of sigma-kernel scratch (two
+// partial sums per point and an arrival counter per tile of 128 points)
+static size_t predict_bytes_per_point(const bk_gp_s* h) { return (size_t)h->n_pad * sizeof(double) + 24; }
 
 // A sigma prediction is a sequence of units (chunk of points, output): K1 writes the K* tiles of the unit, the sigma
 // kernel consumes them.  With two K* buffers K1 of unit u+1 runs beside the sigma kernel of unit u.
@@ -295,14 +296,14 @@ static int lanes_get(bk_gp_s* h) {
 
 // K1 then the sigma kernel of one unit, each on the stream of its lane
 static int predict_unit(bk_gp_s* h, int q, const double* pts, long cnt, double* mean, double* std_out, double* kstar,
-                        int* fail_flag, cudaStream_t s1, cudaStream_t s2, cudaEvent_t between) {
+                        double* scratch, int* fail_flag, cudaStream_t s1, cudaStream_t s2, cudaEvent_t between) {
     if (h->var_mode >= 1) {
         const GpOutput& o = h->out[q];
         const double kappa = pow2_at_least(o.kmax * 1.000001);   // |k| <= (|c0| + |c1| or sum |coef_t|)(1 + few eps) < kappa
         const int scheme = h->var_mode - 1;
         if (int rc = launch_predict(h, q, pts, cnt, mean, nullptr, (int8_t*)kstar, scheme, kappa, s1)) return rc;
         if (between) { BK_CUDA(cudaEventRecord(between, s1)); BK_CUDA(cudaStreamWaitEvent(s2, between, 0)); }
-        return launch_var_ozaki(h, q, scheme, (const int8_t*)kstar, kappa, cnt, std_out, fail_flag, s2);
+        return launch_var_ozaki(h, q, scheme, (const int8_t*)kstar, kappa, cnt, std_out, scratch, fail_flag, s2);
     }
     if (int rc = launch_predict(h, q, pts, cnt, mean, kstar, nullptr, 0, 1.0, s1)) return rc;
     if (between) { BK_CUDA(cudaEventRecord(between, s1)); BK_CUDA(cudaStreamWaitEvent(s2, between, 0)); }
@@ -369,12 +370,13 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
     }
     if (chunk > k_al) chunk = k_al;
     double* kbuf[2] = {(double*)ws, (double*)(ws + (size_t)chunk * per_point)};
+    const size_t kdoubles = (size_t)chunk * h->n_pad;          // the sigma-kernel scratch follows the K* tiles of a buffer
     if (nbuf == 1) {
         for (long lo = 0; lo < k; lo += chunk) {
             const long cnt = (k - lo) < chunk ? (k - lo) : chunk;
             for (int q = 0; q < h->m; ++q)
                 if (int rc = predict_unit(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, std_dev + lo * h->m,
-                                          kbuf[0], fail_flag, st, st, nullptr)) return rc;
+                                          kbuf[0], kbuf[0] + kdoubles, fail_flag, st, st, nullptr)) return rc;
         }
         return 0;
     }
@@ -390,7 +392,7 @@ int bk_gp_predict(bk_gp_t h, const double* pts_dev, long k, double* mean_dev, do
             const int b = (int)(u & 1);
             if (u >= 2) BK_CUDA(cudaStreamWaitEvent(L->k1, L->k2done[b], 0));   // the sigma kernel of unit u-2 released K* buffer b
             if (int rc = predict_unit(h, q, pts_dev + lo * h->p, cnt, mean_dev + lo * h->m, std_dev + lo * h->m,
-                                      kbuf[b], fail_flag, L->k1, L->k2, L->k1done[b])) return rc;
+                                      kbuf[b], kbuf[b] + kdoubles, fail_flag, L->k1, L->k2, L->k1done[b])) return rc;
             BK_CUDA(cudaEventRecord(L->k2done[b], L->k2));
         }
     }

@@ -7,7 +7,11 @@
 // D_g is an int32 accumulation of int8 products (exact for n <= 16384); the 36 slice pairs with a+b <= 9
 // reproduce float64 accuracy (profiles/r01_ozaki_feasibility.md).  Same contract as k_var_trmm (gp_var.cu).
 //
-// One CTA = 128 test points (TMEM lanes, M side = K* slices) against 64-row panels of W (N side), ONE pass over
+// A PAIR of CTAs = 128 test points (TMEM lanes, M side = K* slices) against 64-row panels of W (N side): CTA 2t takes the
+// panels 0, 3 (mod 4) of tile t, CTA 2t+1 the panels 1, 2 (mod 4) -- the same number of k slabs each, because W is
+// lower triangular and panel P runs 2 (P + 1) slabs.  The two CTAs are dispatched together and re-read the same K*
+// tile, so only HALF as many K* tiles (0.9 MB each at n = 1024) are live at a time and the re-reads stay in L2; the
+// CTA that finishes second adds the two partial sums of v^2 in a fixed order.  ONE pass over
 // K per panel: all accumulator groups D_2..D_9 of the 128 x 64 tile are resident in TMEM at once, group g in columns
 // [64 (g-2), 64 (g-1)) -- 448 or 512 of the 512 columns.  The slices of a W panel are stacked along N in shared
 // memory ([slice][64 rows][32 B], 8-row core-matrix groups 256 B apart), so ONE tcgen05.mma of K* slice b against
@@ -122,6 +126,7 @@ template <int SCHEME>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, const int8_t* __restrict__ kq,
             int n_pad, double kappa, double kdiag, double y_std, double* __restrict__ std_out, long k, int ld, int q,
+            double* __restrict__ partial /* [tiles][2][128] */, int* __restrict__ arrived /* [tiles], zeroed */,
             int* __restrict__ fail_flag) {
     constexpr int S = OzTraits<SCHEME>::S;
     constexpr int NG = OzTraits<SCHEME>::G_END - 2;                  // accumulator groups (8 or 7)
@@ -137,8 +142,13 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
     __shared__ volatile int fail_s;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_panels = n_pad / OZ_PANEL, nks = n_pad / 32;
-    const int8_t* kt = kq + (size_t)blockIdx.x * nks * OZ_S * OZ_KTILE;
+    const int nks = n_pad / 32;
+    const int tile = blockIdx.x >> 1, half_cta = blockIdx.x & 1;
+    // panels of this CTA: i-th one = 4 (i / 2) + {0, 3} (CTA 0) or {1, 2} (CTA 1); n_pad / 64 is even
+    const int n_mine = n_pad / OZ_PANEL / 2;
+    auto my_panel = [&](int i) { return 4 * (i >> 1) + (half_cta == 0 ? ((i & 1) ? 3 : 0) : 1 + (i & 1)); };
+    const int8_t* kt = kq + (size_t)tile * nks * OZ_S * OZ_KTILE;
+    __shared__ int last_s;
 
     if (tid == 0) {
         for (int s = 0; s < OZ_SLOTS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -161,7 +171,8 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
         if (lane == 0) {
             int fail = 0;
             long u = 0;                                                      // running slot-use counter
-            for (int panel = 0; panel < n_panels && !fail; ++panel)
+            for (int pi = 0; pi < n_mine && !fail; ++pi) {
+                const int panel = my_panel(pi);
                 for (int ks = 0; ks < (panel + 1) * 2; ++ks, ++u) {
                     const int s = (int)(u % OZ_SLOTS);
                     if (u >= OZ_SLOTS && !oz_wait(&empty[s], (uint32_t)(((u / OZ_SLOTS) - 1) & 1), &fail, &fail_s)) break;
@@ -170,6 +181,7 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
                     tma_load_1d(dst, kt + (size_t)ks * OZ_S * OZ_KTILE, S * OZ_KTILE, &full[s]);
                     tma_load_1d(dst + OZ_SLOT_W, wq + ((size_t)panel * nks + ks) * OZ_S * OZ_WTILE, S * OZ_WTILE, &full[s]);
                 }
+            }
             if (fail) fail_s = 1;
         }
     } else if (warp == 4) {
@@ -177,8 +189,9 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
         if (lane == 0) {
             int fail = 0;
             long u = 0;
-            for (int panel = 0; panel < n_panels && !fail; ++panel) {
-                if (panel > 0 && !oz_wait(acc_empty, (uint32_t)((panel - 1) & 1), &fail, &fail_s)) break;
+            for (int pi = 0; pi < n_mine && !fail; ++pi) {
+                const int panel = my_panel(pi);
+                if (pi > 0 && !oz_wait(acc_empty, (uint32_t)((pi - 1) & 1), &fail, &fail_s)) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int ks = 0; ks < (panel + 1) * 2; ++ks, ++u) {
                     const int s = (int)(u % OZ_SLOTS);
@@ -225,12 +238,13 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
         };
         // After a fault the loop keeps its shape (every epilogue warp meets the named barrier the same number of
         // times) and only the work is skipped.
-        for (int panel = 0; panel < n_panels; ++panel) {
+        for (int pi = 0; pi < n_mine; ++pi) {
+            const int panel = my_panel(pi);
             // row scales of this panel, double buffered: one named barrier per panel among the 8 epilogue warps
-            double* sg = sigs + (panel & 1) * OZ_PANEL;
+            double* sg = sigs + (pi & 1) * OZ_PANEL;
             if (half == 0 && tp < OZ_PANEL) sg[tp] = wsig[panel * OZ_PANEL + tp] * kappa;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (!oz_wait(acc_full, (uint32_t)(panel & 1), &fail, &fail_s)) continue;
+            if (!oz_wait(acc_full, (uint32_t)(pi & 1), &fail, &fail_s)) continue;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // 4 chunks of 8 W rows, software pipelined: the TMEM read of chunk c+1 flies under the arithmetic of
             // chunk c (tcgen05.wait::ld waits for everything issued so far)
@@ -259,10 +273,18 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-    if (tid < 128) {
-        const long t = (long)blockIdx.x * 128 + tid;
+    // this CTA's share of sum v^2 per test point; the CTA of the pair that arrives second finishes the tile
+    if (tid < 128) partial[((size_t)tile * 2 + half_cta) * 128 + tid] = colred[tid] + colred[128 + tid];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) last_s = atomicAdd(&arrived[tile], 1);
+    __syncthreads();
+    if (last_s == 1 && tid < 128) {
+        __threadfence();
+        const long t = (long)tile * 128 + tid;
         if (t < k) {
-            double var = __dadd_rn(kdiag, -(colred[tid] + colred[128 + tid]));         // sklearn:_gpr.py:480-481
+            const volatile double* pt = partial + (size_t)tile * 2 * 128;
+            double var = __dadd_rn(kdiag, -(pt[tid] + pt[128 + tid]));                 // sklearn:_gpr.py:480-481
             if (var < 0.0) var = 0.0;                                                  // :485-491
             std_out[t * ld + q] = sqrt(__dmul_rn(var, __dmul_rn(y_std, y_std)));       // :494,500
         }
@@ -327,7 +349,7 @@ int launch_slice_w(const double* src, int n, int ld, int transposed, int scheme,
 }
 
 int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, double kappa, long k, double* std_out,
-                     int* fail_flag, cudaStream_t st) {
+                     double* scratch, int* fail_flag, cudaStream_t st) {
     const GpOutput& o = h->out[q];
     if (!o.wq || !o.wsig) return set_error("int8 variance path requested but output %d has no sliced L^-1", q);
     static OncePerDevice attr_set;
@@ -335,14 +357,18 @@ int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, doub
         BK_CUDA(cudaFuncSetAttribute(k_var_ozaki<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
         BK_CUDA(cudaFuncSetAttribute(k_var_ozaki<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
     }
-    const unsigned grid = (unsigned)((k + 127) / 128);
+    // scratch: [tiles][2][128] partial sums, then [tiles] arrival counters
+    const unsigned tiles = (unsigned)((k + 127) / 128), grid = 2 * tiles;
+    double* partial = scratch;
+    int* arrived = reinterpret_cast<int*>(scratch + (size_t)tiles * 256);
+    BK_CUDA(cudaMemsetAsync(arrived, 0, sizeof(int) * tiles, st));
     ProfScope prof(PROF_VAR, st);
     if (scheme == 1)
         k_var_ozaki<1><<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std,
-                                                          std_out, k, h->m, q, fail_flag);
+                                                          std_out, k, h->m, q, partial, arrived, fail_flag);
     else
         k_var_ozaki<0><<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std,
-                                                          std_out, k, h->m, q, fail_flag);
+                                                          std_out, k, h->m, q, partial, arrived, fail_flag);
     BK_LAUNCH_CHECK("k_var_ozaki");
     return 0;
 }

@@ -422,14 +422,18 @@ class UQ:
         d['S1_selected'], d['ST_selected'] = d[key[0]], d[key[1]]
         d['S1_agg_selected'], d['ST_agg_selected'] = d[key[0] + '_agg'], d[key[1] + '_agg']
         self._intervals(lib, partials, totals, kept, keep_basis, size, p, F, second, nslots, world, stream)
-        self.logger.debug("-> Second order:\n{}\n".format(d['S2']))
-        self.logger.debug("-> First order:\n{}\n-> Total:\n{}\n".format(d['S1_selected'], d['ST_selected']))
+        # the messages of uq.py:376-378, 427-436; formatted only when somebody listens (array formatting costs
+        # milliseconds, more than a small Saltelli pass)
+        if self.logger.isEnabledFor(logging.DEBUG):
+            self.logger.debug("-> Second order:\n{}\n".format(d['S2']))
+            self.logger.debug("-> First order:\n{}\n-> Total:\n{}\n".format(d['S1_selected'], d['ST_selected']))
         if self.type_indices == 'aggregated':
             aggregated = [d['S2_agg'], d['S1_agg_selected'], d['ST_agg_selected']]
-            self.logger.info("-> First order confidence:\n{}\n-> Total order confidence:\n{}\n"
-                             .format(d['S1_interval'], d['ST_interval']))
-            self.logger.info("Aggregated_indices:\n-> Second order:\n{}\n-> First order:\n{}\n-> Total order:\n{}\n"
-                             .format(*aggregated))
+            if self.logger.isEnabledFor(logging.INFO):
+                self.logger.info("-> First order confidence:\n{}\n-> Total order confidence:\n{}\n"
+                                 .format(d['S1_interval'], d['ST_interval']))
+                self.logger.info("Aggregated_indices:\n-> Second order:\n{}\n-> First order:\n{}\n-> Total order:\n{}\n"
+                                 .format(*aggregated))
         else:
             aggregated = [d['S2'][0], d['S1_selected'][0], d['ST_selected'][0]]            # uq.py:466-468
         self._write_files(d, p, F)
@@ -471,18 +475,21 @@ class UQ:
                     r = R.shape[0]
                 _lib.check(lib.bk_sobol_asymptotic(ctypes.c_void_p(z.data_ptr()), cnt, cnt, p, r,
                                                    ctypes.c_void_p(c_d.data_ptr()), ctypes.c_void_p(asym.data_ptr()), stream))
+        # one buffer for the interval sums: [asymptotic sums | number of ranks that kept their outputs], summed over the
+        # ranks in ONE all-reduce beside the all-gather of the jackknife groups; ONE device -> host copy for both
+        na = (2 + 6 * p) * 2
+        abuf = torch.zeros(na + 1, dtype=torch.float64, device=dev)
+        if asym is not None:
+            abuf[:na] = asym.reshape(-1)
+            abuf[na] = 1.0
         if world > 1:
             parts = [torch.empty_like(jk) for _ in range(world)]
             dist.all_gather(parts, jk)
             jk = torch.cat(parts, dim=0)
-            flag = torch.tensor([1.0 if asym is not None else 0.0], dtype=torch.float64, device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)                 # every rank kept its outputs, or none is used
-            if asym is None:
-                asym = torch.zeros((2 + 6 * p, 2), dtype=torch.float64, device=dev)
-            dist.all_reduce(asym, op=dist.ReduceOp.SUM)
-            if float(flag.item()) == 0.0:
-                asym = None
-        jk = jk.cpu().numpy()
+            dist.all_reduce(abuf, op=dist.ReduceOp.SUM)
+        host = torch.cat([abuf, jk.reshape(-1)]).cpu().numpy()
+        asym = host[:na].reshape(2 + 6 * p, 2) if host[na] == float(world) else None   # every rank kept its outputs, or none is used
+        jk = host[na + 1:].reshape(-1, 2 + 2 * p)
         jk = jk[jk[:, 0] > 0]
         theta = np.concatenate([d['S1_agg'], d['ST_agg']])
         G = len(jk)
@@ -497,8 +504,7 @@ class UQ:
         d['S1_agg_sigma_jackknife'], d['ST_agg_sigma_jackknife'] = sigma_jk[:p], sigma_jk[p:]
         d['jackknife_groups'] = G
         if asym is not None:
-            a = asym.cpu().numpy()
-            s1, st = asymptotic_sigma(a[:, 0] + a[:, 1], size, p)
+            s1, st = asymptotic_sigma(asym[:, 0] + asym[:, 1], size, p)
             d['S1_agg_sigma_asymptotic'], d['ST_agg_sigma_asymptotic'] = s1, st
             d['interval_method'] = 'asymptotic'
             sigma = np.concatenate([s1, st])

@@ -354,3 +354,40 @@ def test_pipelined_host_path_matches_single_call():
     assert np.array_equal(mean, dm.cpu().numpy()) and np.array_equal(std, ds.cpu().numpy())
     mean2, none = model.predict(pts, return_std=False)
     assert none is None and np.array_equal(mean2, mean)
+
+
+@pytest.mark.parametrize('scheme', [0, 1])
+def test_int8_slicing_of_w_rows_with_wide_dynamic_range(scheme):
+    """The int8 path slices every row of W = L^-1 in fixed point relative to the row's largest entry.  A
+    near-singular K (short-range RBF, pairs of training points 1e-5 apart, cond(K) ~ 1/jitter) gives rows of W whose entries span
+    more than 2^40; the variance from the slices must then be as close to the long-double value as the FP64 DMMA
+    kernel's is (56 bits of fixed point against 53 bits of floating point per product, exact accumulation against
+    rounded accumulation)."""
+    import torch
+    from oracle import functions as ofun
+    rng = np.random.RandomState(5)
+    p, n0 = 2, 160
+    X0 = ofun.halton(n0, p)
+    X = np.vstack([X0, X0[:48] + 1e-5 * rng.randn(48, p)])
+    y = np.sin(5 * X[:, 0]) * np.cos(3 * X[:, 1])
+    st = ogp.fit_state(('prod', ('const', 1.0), ('rbf', np.full(p, 0.07))), X, y)
+    rows = np.abs(np.linalg.inv(st['L']))
+    span = [rows[i, :i + 1].max() / rows[i, :i + 1][rows[i, :i + 1] > 0].min() for i in range(1, len(rows))]
+    assert max(span) > 2.0 ** 40, "the case must exercise a wide row"
+    k = kriging_from_states([st])
+    model = k._model()
+    pts = np.vstack([rng.rand(96, p), X[:16] + 3e-6, X[n0:n0 + 16] - 2e-6])
+    model.set_sigma_kernel('dmma')
+    _, s_f = k.evaluate(pts)
+    model.set_int8_scheme(scheme)
+    model.set_sigma_kernel('int8')
+    _, s_i = k.evaluate(pts)
+    _, sld = gp_hp.predict_hp(st, pts)
+    ref = (sld ** 2).astype(float)
+    prior = ogp.kernel_diag(st['tree']) * st['y_std'] ** 2
+    err_i = np.max(np.abs(s_i[:, 0] ** 2 - ref)) / prior
+    err_f = np.max(np.abs(s_f[:, 0] ** 2 - ref)) / prior
+    print("max |W| %.2e, widest row span 2^%.0f: int8 scheme %d vs long double %.2e, FP64 DMMA vs long double %.2e "
+          "(of the prior variance)" % (rows.max(), np.log2(max(span)), scheme, err_i, err_f))
+    assert err_i <= max(4.0 * err_f, 1e-12)
+    torch.cuda.synchronize()

@@ -143,11 +143,15 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nks = n_pad / 32;
-    const int tile = blockIdx.x >> 1, half_cta = blockIdx.x & 1;
+    // Persistent CTAs: the grid is an even number of CTAs (<= the SM count); CTA b walks the tiles b/2, b/2 + grid/2,
+    // ... and always takes the same half of their panels, so the two CTAs of a pair stay on the same tile.  The
+    // mbarrier ring, the accumulator hand-shake and TMEM live across tiles: the producer is already filling the
+    // first slabs of the next tile while the epilogue drains the last panel of this one.
+    const int half_cta = blockIdx.x & 1, tile0 = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+    const int n_tiles = (int)((k + 127) / 128);
     // panels of this CTA: i-th one = 4 (i / 2) + {0, 3} (CTA 0) or {1, 2} (CTA 1); n_pad / 64 is even
     const int n_mine = n_pad / OZ_PANEL / 2;
     auto my_panel = [&](int i) { return 4 * (i >> 1) + (half_cta == 0 ? ((i & 1) ? 3 : 0) : 1 + (i & 1)); };
-    const int8_t* kt = kq + (size_t)tile * nks * OZ_S * OZ_KTILE;
     __shared__ int last_s;
 
     if (tid == 0) {
@@ -171,7 +175,9 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
         if (lane == 0) {
             int fail = 0;
             long u = 0;                                                      // running slot-use counter
-            for (int pi = 0; pi < n_mine && !fail; ++pi) {
+            for (int tile = tile0; tile < n_tiles && !fail; tile += tile_step) {
+              const int8_t* kt = kq + (size_t)tile * nks * OZ_S * OZ_KTILE;
+              for (int pi = 0; pi < n_mine && !fail; ++pi) {
                 const int panel = my_panel(pi);
                 for (int ks = 0; ks < (panel + 1) * 2; ++ks, ++u) {
                     const int s = (int)(u % OZ_SLOTS);
@@ -181,6 +187,7 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
                     tma_load_1d(dst, kt + (size_t)ks * OZ_S * OZ_KTILE, S * OZ_KTILE, &full[s]);
                     tma_load_1d(dst + OZ_SLOT_W, wq + ((size_t)panel * nks + ks) * OZ_S * OZ_WTILE, S * OZ_WTILE, &full[s]);
                 }
+              }
             }
             if (fail) fail_s = 1;
         }
@@ -189,9 +196,11 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
         if (lane == 0) {
             int fail = 0;
             long u = 0;
-            for (int pi = 0; pi < n_mine && !fail; ++pi) {
+            int rnd = 0;                                                     // panels issued so far, over all tiles
+            for (int tile = tile0; tile < n_tiles && !fail; tile += tile_step)
+              for (int pi = 0; pi < n_mine && !fail; ++pi, ++rnd) {
                 const int panel = my_panel(pi);
-                if (pi > 0 && !oz_wait(acc_empty, (uint32_t)((pi - 1) & 1), &fail, &fail_s)) break;
+                if (rnd > 0 && !oz_wait(acc_empty, (uint32_t)((rnd - 1) & 1), &fail, &fail_s)) break;
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int ks = 0; ks < (panel + 1) * 2; ++ks, ++u) {
                     const int s = (int)(u % OZ_SLOTS);
@@ -238,13 +247,15 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
         };
         // After a fault the loop keeps its shape (every epilogue warp meets the named barrier the same number of
         // times) and only the work is skipped.
-        for (int pi = 0; pi < n_mine; ++pi) {
+        int rnd = 0;                                        // panels drained so far, over all tiles
+        for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+          for (int pi = 0; pi < n_mine; ++pi, ++rnd) {
             const int panel = my_panel(pi);
             // row scales of this panel, double buffered: one named barrier per panel among the 8 epilogue warps
-            double* sg = sigs + (pi & 1) * OZ_PANEL;
+            double* sg = sigs + (rnd & 1) * OZ_PANEL;
             if (half == 0 && tp < OZ_PANEL) sg[tp] = wsig[panel * OZ_PANEL + tp] * kappa;
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            if (!oz_wait(acc_full, (uint32_t)(pi & 1), &fail, &fail_s)) continue;
+            if (!oz_wait(acc_full, (uint32_t)(rnd & 1), &fail, &fail_s)) continue;
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // 4 chunks of 8 W rows, software pipelined: the TMEM read of chunk c+1 flies under the arithmetic of
             // chunk c (tcgen05.wait::ld waits for everything issued so far)
@@ -266,29 +277,34 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_empty);
             process_chunk(db, sgh + 24);
+          }
+          // ---- end of this CTA's share of the tile: the two column halves meet in shared memory, the share goes to
+          // global memory, and the CTA of the pair that arrives second finishes the tile in a fixed order
+          colred[half * 128 + tp] = vsum;
+          vsum = 0.0;
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (half == 0) partial[((size_t)tile * 2 + half_cta) * 128 + tp] = colred[tp] + colred[128 + tp];
+          __threadfence();
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (half == 0 && tp == 0) last_s = atomicAdd(&arrived[tile], 1);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (last_s == 1 && half == 0) {
+              __threadfence();
+              const long t = (long)tile * 128 + tp;
+              if (t < k) {
+                  const volatile double* pt = partial + (size_t)tile * 2 * 128;
+                  double var = __dadd_rn(kdiag, -(pt[tp] + pt[128 + tp]));                   // sklearn:_gpr.py:480-481
+                  if (var < 0.0) var = 0.0;                                                  // :485-491
+                  std_out[t * ld + q] = sqrt(__dmul_rn(var, __dmul_rn(y_std, y_std)));       // :494,500
+              }
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");      // colred and last_s are free for the next tile
         }
         if (fail) fail_s = 1;
-        colred[half * 128 + tp] = vsum;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
-    // this CTA's share of sum v^2 per test point; the CTA of the pair that arrives second finishes the tile
-    if (tid < 128) partial[((size_t)tile * 2 + half_cta) * 128 + tid] = colred[tid] + colred[128 + tid];
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) last_s = atomicAdd(&arrived[tile], 1);
-    __syncthreads();
-    if (last_s == 1 && tid < 128) {
-        __threadfence();
-        const long t = (long)tile * 128 + tid;
-        if (t < k) {
-            const volatile double* pt = partial + (size_t)tile * 2 * 128;
-            double var = __dadd_rn(kdiag, -(pt[tid] + pt[128 + tid]));                 // sklearn:_gpr.py:480-481
-            if (var < 0.0) var = 0.0;                                                  // :485-491
-            std_out[t * ld + q] = sqrt(__dmul_rn(var, __dmul_rn(y_std, y_std)));       // :494,500
-        }
-    }
     if (tid == 0 && fail_s) *fail_flag = 1;
 }
 
@@ -358,7 +374,14 @@ int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, doub
         BK_CUDA(cudaFuncSetAttribute(k_var_ozaki<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
     }
     // scratch: [tiles][2][128] partial sums, then [tiles] arrival counters
-    const unsigned tiles = (unsigned)((k + 127) / 128), grid = 2 * tiles;
+    const unsigned tiles = (unsigned)((k + 127) / 128);
+    static int sm_count[64] = {};
+    int dev = 0;
+    BK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return set_error("device ordinal %d out of range", dev);
+    if (!sm_count[dev]) BK_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
+    const unsigned pairs = (unsigned)sm_count[dev] / 2;               // one CTA per SM: persistent CTA pairs
+    const unsigned grid = 2 * (tiles < pairs ? tiles : pairs);
     double* partial = scratch;
     int* arrived = reinterpret_cast<int*>(scratch + (size_t)tiles * 256);
     BK_CUDA(cudaMemsetAsync(arrived, 0, sizeof(int) * tiles, st));

@@ -600,13 +600,16 @@ def main():
     def e2e_time(arr, tag):
         surrogate(arr)                                          # one untimed full-size call: staging buffers, streams
         times = []
-        for _ in range(max(1, min(args.steps, 3))):
+        for _ in range(max(1, min(args.steps, 5))):
             _barrier(cx)
             t0 = time.perf_counter()
             surrogate(arr)
             times.append(time.perf_counter() - t0)
         e2e_runs[tag] = [round(t, 4) for t in times]
-        return _max_over_ranks(cx, float(np.mean(times)))
+        # median of the calls, every call listed in `runs_s`: about one pageable call in four stalls for ~0.2 s on
+        # these hosts, on every rank at once and whatever the staging scheme (profiles/r02_e2e_probe_4gpu.jsonl); the
+        # same call fed from pinned memory never does
+        return _max_over_ranks(cx, float(np.median(times)))
     e2e_value = world * e2e_rows / e2e_time(host_np, 'pageable')
     host_pin = torch.empty((e2e_rows, P_DIM), dtype=torch.float64, pin_memory=True)
     host_pin.copy_(D)
@@ -726,7 +729,8 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(e2e_rows * P_DIM * 8),
                     "d2h_bytes_per_step": int(e2e_rows * 2 * 8),
-                    "api": "SurrogateModel.__call__ (pageable numpy in, numpy out)", "runs_s": e2e_runs.get('pageable')},
+                    "api": "SurrogateModel.__call__ (pageable numpy in, numpy out)", "runs_s": e2e_runs.get('pageable'),
+                    "statistic": "median of the listed calls (after one untimed call), max over ranks"},
             "e2e_pinned": {"value": e2e_pinned, "unit": unit, "note": "same call fed from a pinned host buffer"},
             "gpu_launches": int(var_launches + pred_launches), "roofline": roofline, "roofline_sobol": roofline_sobol,
             "sobol": {"wall_s": sob_wall, "N": args.n_base * world, "rows": args.n_base * world * nb,

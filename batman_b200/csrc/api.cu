@@ -256,9 +256,9 @@ static double pow2_at_least(double v) {
     return ldexp(1.0, e);
 }
 
-// per point: K* tile bytes (FP64 fragments or 8 int8 slices: both n_pad * 8) + 24 bytes of sigma-kernel scratch (two
-// partial sums per point and an arrival counter per tile of 128 points)
-static size_t predict_bytes_per_point(const bk_gp_s* h) { return (size_t)h->n_pad * sizeof(double) + 24; }
+// per point: K* tile bytes (FP64 fragments or 8 int8 slices: both n_pad * 8) + 304 bytes of sigma-kernel scratch (up to
+// 37 partial sums per point, one per CTA of a gang, and an arrival counter per tile of 128 points)
+static size_t predict_bytes_per_point(const bk_gp_s* h) { return (size_t)h->n_pad * sizeof(double) + 304; }
 
 // A sigma prediction is a sequence of units (chunk of points, output): K1 writes the K* tiles of the unit, the sigma
 // kernel consumes them.  With two K* buffers K1 of unit u+1 runs beside the sigma kernel of unit u.

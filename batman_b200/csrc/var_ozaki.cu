@@ -7,11 +7,12 @@
 // D_g is an int32 accumulation of int8 products (exact for n <= 16384); the 36 slice pairs with a+b <= 9
 // reproduce float64 accuracy (profiles/r01_ozaki_feasibility.md).  Same contract as k_var_trmm (gp_var.cu).
 //
-// A PAIR of CTAs = 128 test points (TMEM lanes, M side = K* slices) against 64-row panels of W (N side): CTA 2t takes the
-// panels 0, 3 (mod 4) of tile t, CTA 2t+1 the panels 1, 2 (mod 4) -- the same number of k slabs each, because W is
-// lower triangular and panel P runs 2 (P + 1) slabs.  The two CTAs are dispatched together and re-read the same K*
-// tile, so only HALF as many K* tiles (0.9 MB each at n = 1024) are live at a time and the re-reads stay in L2; the
-// CTA that finishes second adds the two partial sums of v^2 in a fixed order.  ONE pass over
+// A GANG of G CTAs = 128 test points (TMEM lanes, M side = K* slices) against 64-row panels of W (N side).  The panels
+// are dealt to the G CTAs in snake order (CTA c takes the panels c and 2G-1-c of every run of 2G): the same number
+// of k slabs each, because W is lower triangular and panel P runs 2 (P + 1) slabs.  The CTAs of a gang work at the
+// same time and re-read the same K* tile (n_pad * 896 bytes: 0.9 MB at n = 1024, 3.7 MB at n = 4096) once per
+// panel, so only (SM count / G) tiles are live at a time; G grows with n_train so that they fit in the L2 and the
+// re-reads never reach DRAM.  The CTA that finishes last adds the G partial sums of v^2 in a fixed order.  ONE pass over
 // K per panel: all accumulator groups D_2..D_9 of the 128 x 64 tile are resident in TMEM at once, group g in columns
 // [64 (g-2), 64 (g-1)) -- 448 or 512 of the 512 columns.  The slices of a W panel are stacked along N in shared
 // memory ([slice][64 rows][32 B], 8-row core-matrix groups 256 B apart), so ONE tcgen05.mma of K* slice b against
@@ -61,6 +62,13 @@ __device__ __forceinline__ void oz_mma(uint32_t tmem_d, uint64_t adesc, uint64_t
 }
 __device__ __forceinline__ void oz_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bulk copy with an L2 eviction-priority hint.  The K* tiles of the gangs in flight are the re-read set (once per W
+// panel): evict-last.  W is re-read once per tile by every gang: normal priority while it fits beside the K* tiles,
+// evict-first when it is far larger than the L2 (n_train > ~5000: it streams, and must not push the K* tiles out).
+__device__ __forceinline__ void tma_load_1d_hint(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
 // bounded wait: a mis-programmed pipeline must not hang the GPU box.  A time-out (or a fault recorded by another
 // role in `fail_s`) makes every later wait of the CTA return at once; callers skip their work but keep walking
@@ -126,8 +134,8 @@ template <int SCHEME>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
 k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, const int8_t* __restrict__ kq,
             int n_pad, double kappa, double kdiag, double y_std, double* __restrict__ std_out, long k, int ld, int q,
-            double* __restrict__ partial /* [tiles][2][128] */, int* __restrict__ arrived /* [tiles], zeroed */,
-            int* __restrict__ fail_flag) {
+            double* __restrict__ partial /* [tiles][G][128] */, int* __restrict__ arrived /* [tiles], zeroed */,
+            int G, int w_streams, int* __restrict__ fail_flag) {
     constexpr int S = OzTraits<SCHEME>::S;
     constexpr int NG = OzTraits<SCHEME>::G_END - 2;                  // accumulator groups (8 or 7)
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -143,15 +151,16 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nks = n_pad / 32;
-    // Persistent CTAs: the grid is an even number of CTAs (<= the SM count); CTA b walks the tiles b/2, b/2 + grid/2,
-    // ... and always takes the same half of their panels, so the two CTAs of a pair stay on the same tile.  The
-    // mbarrier ring, the accumulator hand-shake and TMEM live across tiles: the producer is already filling the
-    // first slabs of the next tile while the epilogue drains the last panel of this one.
-    const int half_cta = blockIdx.x & 1, tile0 = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+    // Persistent CTAs: the grid is a whole number of gangs (<= the SM count); CTA b = (gang b / G, member b % G) walks
+    // the tiles gang, gang + gangs, ... and always takes the same share of their panels, so the members of a gang
+    // stay on the same tile.  The mbarrier ring, the accumulator hand-shake and TMEM live across tiles: the producer
+    // is already filling the first slabs of the next tile while the epilogue drains the last panel of this one.
+    const int member = blockIdx.x % G, tile0 = blockIdx.x / G, tile_step = gridDim.x / G;
     const int n_tiles = (int)((k + 127) / 128);
-    // panels of this CTA: i-th one = 4 (i / 2) + {0, 3} (CTA 0) or {1, 2} (CTA 1); n_pad / 64 is even
-    const int n_mine = n_pad / OZ_PANEL / 2;
-    auto my_panel = [&](int i) { return 4 * (i >> 1) + (half_cta == 0 ? ((i & 1) ? 3 : 0) : 1 + (i & 1)); };
+    // panels of this CTA in snake order: i-th one = 2G (i / 2) + (member | 2G - 1 - member), increasing in i
+    auto my_panel = [&](int i) { return 2 * G * (i >> 1) + ((i & 1) ? 2 * G - 1 - member : member); };
+    int n_mine = 0;
+    while (my_panel(n_mine) < n_pad / OZ_PANEL) ++n_mine;
     __shared__ int last_s;
 
     if (tid == 0) {
@@ -175,6 +184,9 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
         if (lane == 0) {
             int fail = 0;
             long u = 0;                                                      // running slot-use counter
+            uint64_t pol_keep, pol_stream;
+            asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
             for (int tile = tile0; tile < n_tiles && !fail; tile += tile_step) {
               const int8_t* kt = kq + (size_t)tile * nks * OZ_S * OZ_KTILE;
               for (int pi = 0; pi < n_mine && !fail; ++pi) {
@@ -184,8 +196,10 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
                     if (u >= OZ_SLOTS && !oz_wait(&empty[s], (uint32_t)(((u / OZ_SLOTS) - 1) & 1), &fail, &fail_s)) break;
                     unsigned char* dst = stages + (size_t)s * OZ_SLOT_BYTES;
                     mbar_expect_tx(&full[s], (uint32_t)(S * (OZ_KTILE + OZ_WTILE)));
-                    tma_load_1d(dst, kt + (size_t)ks * OZ_S * OZ_KTILE, S * OZ_KTILE, &full[s]);
-                    tma_load_1d(dst + OZ_SLOT_W, wq + ((size_t)panel * nks + ks) * OZ_S * OZ_WTILE, S * OZ_WTILE, &full[s]);
+                    tma_load_1d_hint(dst, kt + (size_t)ks * OZ_S * OZ_KTILE, S * OZ_KTILE, &full[s], pol_keep);
+                    const int8_t* w_src = wq + ((size_t)panel * nks + ks) * OZ_S * OZ_WTILE;
+                    if (w_streams) tma_load_1d_hint(dst + OZ_SLOT_W, w_src, S * OZ_WTILE, &full[s], pol_stream);
+                    else tma_load_1d(dst + OZ_SLOT_W, w_src, S * OZ_WTILE, &full[s]);
                 }
               }
             }
@@ -279,21 +293,23 @@ k_var_ozaki(const int8_t* __restrict__ wq, const double* __restrict__ wsig, cons
             process_chunk(db, sgh + 24);
           }
           // ---- end of this CTA's share of the tile: the two column halves meet in shared memory, the share goes to
-          // global memory, and the CTA of the pair that arrives second finishes the tile in a fixed order
+          // global memory, and the member of the gang that arrives last finishes the tile in a fixed order
           colred[half * 128 + tp] = vsum;
           vsum = 0.0;
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (half == 0) partial[((size_t)tile * 2 + half_cta) * 128 + tp] = colred[tp] + colred[128 + tp];
+          if (half == 0) partial[((size_t)tile * G + member) * 128 + tp] = colred[tp] + colred[128 + tp];
           __threadfence();
           asm volatile("bar.sync 1, 256;" ::: "memory");
           if (half == 0 && tp == 0) last_s = atomicAdd(&arrived[tile], 1);
           asm volatile("bar.sync 1, 256;" ::: "memory");
-          if (last_s == 1 && half == 0) {
+          if (last_s == G - 1 && half == 0) {
               __threadfence();
               const long t = (long)tile * 128 + tp;
               if (t < k) {
-                  const volatile double* pt = partial + (size_t)tile * 2 * 128;
-                  double var = __dadd_rn(kdiag, -(pt[tp] + pt[128 + tp]));                   // sklearn:_gpr.py:480-481
+                  const volatile double* pt = partial + (size_t)tile * G * 128;
+                  double vv = pt[tp];
+                  for (int c = 1; c < G; ++c) vv += pt[c * 128 + tp];                         // fixed order: member 0, 1, ...
+                  double var = __dadd_rn(kdiag, -vv);                                        // sklearn:_gpr.py:480-481
                   if (var < 0.0) var = 0.0;                                                  // :485-491
                   std_out[t * ld + q] = sqrt(__dmul_rn(var, __dmul_rn(y_std, y_std)));       // :494,500
               }
@@ -364,6 +380,17 @@ int launch_slice_w(const double* src, int n, int ld, int transposed, int scheme,
     return 0;
 }
 
+// CTAs per tile of test points: the live K* tiles ((SMs / G) x n_pad x 896 bytes) should fit in about half of the L2
+// (126 MB on B200); candidates are the sizes that leave at most four SMs without a gang on 148 SMs.
+int oz_gang_size(int n_pad, int sms) {
+    const int cand[] = {2, 4, 8, 16, 37};
+    const double budget = 72e6, tile_bytes = (double)n_pad * 128.0 * 7.0;
+    for (int g : cand)
+        if (g <= sms && (double)(sms / g) * tile_bytes <= budget) return g;
+    return sms >= 37 ? 37 : 2;
+}
+constexpr int OZ_GANG_MAX = 37;
+
 int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, double kappa, long k, double* std_out,
                      double* scratch, int* fail_flag, cudaStream_t st) {
     const GpOutput& o = h->out[q];
@@ -373,25 +400,28 @@ int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, doub
         BK_CUDA(cudaFuncSetAttribute(k_var_ozaki<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
         BK_CUDA(cudaFuncSetAttribute(k_var_ozaki<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM));
     }
-    // scratch: [tiles][2][128] partial sums, then [tiles] arrival counters
+    // scratch: [tiles][G][128] partial sums, then [tiles] arrival counters
     const unsigned tiles = (unsigned)((k + 127) / 128);
     static int sm_count[64] = {};
     int dev = 0;
     BK_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return set_error("device ordinal %d out of range", dev);
     if (!sm_count[dev]) BK_CUDA(cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev));
-    const unsigned pairs = (unsigned)sm_count[dev] / 2;               // one CTA per SM: persistent CTA pairs
-    const unsigned grid = 2 * (tiles < pairs ? tiles : pairs);
+    const int G = oz_gang_size(h->n_pad, sm_count[dev]);
+    unsigned gangs = (unsigned)(sm_count[dev] / G);                   // one CTA per SM: persistent gangs
+    if (gangs > tiles) gangs = tiles;
+    const unsigned grid = gangs * (unsigned)G;
     double* partial = scratch;
-    int* arrived = reinterpret_cast<int*>(scratch + (size_t)tiles * 256);
+    int* arrived = reinterpret_cast<int*>(scratch + (size_t)tiles * G * 128);
     BK_CUDA(cudaMemsetAsync(arrived, 0, sizeof(int) * tiles, st));
+    const int w_streams = (double)h->n_pad * h->n_pad * 3.5 > 100e6 ? 1 : 0;       // bytes of the lower triangle's slices
     ProfScope prof(PROF_VAR, st);
     if (scheme == 1)
         k_var_ozaki<1><<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std,
-                                                          std_out, k, h->m, q, partial, arrived, fail_flag);
+                                                          std_out, k, h->m, q, partial, arrived, G, w_streams, fail_flag);
     else
         k_var_ozaki<0><<<grid, OZ_THREADS, OZ_SMEM, st>>>(o.wq, o.wsig, kq, h->n_pad, kappa, o.kdiag, o.y_std,
-                                                          std_out, k, h->m, q, partial, arrived, fail_flag);
+                                                          std_out, k, h->m, q, partial, arrived, G, w_streams, fail_flag);
     BK_LAUNCH_CHECK("k_var_ozaki");
     return 0;
 }

@@ -344,6 +344,7 @@ class UQ:
                 if pod is None and not block:
                     # fused path: design -> mean -> products -> (hi, lo) sums; the field of outputs is never stored
                     shift = _lib.as_double_array(model.y_means)
+                    ymeans_dev = torch.tensor(list(model.y_means), dtype=torch.float64, device=dev)   # before the long kernel
                     a_p = ptr(A_all[lo:hi]) if A_all is not None else None
                     b_p = ptr(B_all[lo:hi]) if B_all is not None else None
                     if keep and hi > lo:
@@ -408,10 +409,28 @@ class UQ:
             allreduce_totals(totals)
         out = torch.empty(lib.bk_sobol_result_len(p, F), dtype=torch.float64, device=dev)
         _lib.check(lib.bk_sobol_finalize(ptr(totals), size, p, F, second, ptr(out), stream))
-        res = out.cpu().numpy()
+        # When the kept outputs ARE the estimator's outputs (fused path, ensemble mode) their centre is the mean over all
+        # rows, which finalize just left on the device: the interval kernels and collectives are queued first and the
+        # call ends with ONE device -> host read.  With a basis in between (POD field, block integral) the centre
+        # needs a small host solve, so the indices are read first.
+        nres = out.numel()
+        center_dev = None
+        if kept and keep_basis is None:
+            center_dev = out[nres - F:] + (shift_f if self.surrogate is None else ymeans_dev)
+        isums = None
+        if center_dev is not None or not kept:
+            abuf, jk = self._interval_sums(lib, partials, totals, kept, center_dev, None, size, p, F, second, nslots,
+                                           world, stream)
+            tail = [center_dev] if center_dev is not None else []
+            host = torch.cat([out, abuf, jk.reshape(-1)] + tail).cpu().numpy()
+            res, isums = host[:nres], host[nres:nres + abuf.numel() + jk.numel()]
+        else:
+            res = out.cpu().numpy()
         self.details = d = self._unpack(res, p, F)
         # mean of every estimator output over all rows (the centring of the estimator)
-        if self.surrogate is None:
+        if center_dev is not None:
+            d['mean'] = host[nres + len(isums):].copy()
+        elif self.surrogate is None:
             d['mean'] = d['mean'] + shift_f.cpu().numpy()
         elif keep_basis is None:
             d['mean'] = d['mean'] + np.asarray(self.surrogate.predictor._model().y_means)
@@ -421,7 +440,12 @@ class UQ:
                'mauntz-kucherenko': ('S1_mauntz_kucherenko', 'ST_mauntz_kucherenko')}[self.estimator]
         d['S1_selected'], d['ST_selected'] = d[key[0]], d[key[1]]
         d['S1_agg_selected'], d['ST_agg_selected'] = d[key[0] + '_agg'], d[key[1] + '_agg']
-        self._intervals(lib, partials, totals, kept, keep_basis, size, p, F, second, nslots, world, stream)
+        if isums is None:
+            center, R = self._interval_geometry(d, keep_basis, kept[0][0].shape[2])
+            c_d = torch.from_numpy(np.ascontiguousarray(center)).to(dev)
+            abuf, jk = self._interval_sums(lib, partials, totals, kept, c_d, R, size, p, F, second, nslots, world, stream)
+            isums = torch.cat([abuf, jk.reshape(-1)]).cpu().numpy()
+        self._interval_finish(isums, size, p, world)
         # the messages of uq.py:376-378, 427-436; formatted only when somebody listens (array formatting costs
         # milliseconds, more than a small Saltelli pass)
         if self.logger.isEnabledFor(logging.DEBUG):
@@ -444,27 +468,26 @@ class UQ:
             self.error_model(aggregated, self.test)
         return aggregated
 
-    def _intervals(self, lib, partials, totals, kept, keep_basis, size, p, F, second, nslots, world, stream):
-        """95 % intervals of the aggregated first / total order indices (uq.py:341, 425-426).
+    def _interval_sums(self, lib, partials, totals, kept, c_d, R, size, p, F, second, nslots, world, stream):
+        """Device half of the 95 % intervals of the aggregated first / total order indices (uq.py:341, 425-426):
+        -> (abuf, jk) device tensors, summed / gathered over the ranks, nothing read back.
 
         ``asymptotic``: the delta-method intervals the reference asks OpenTURNS for, from the kept block outputs and
-        the exact centring (``bk_sobol_asymptotic``; formulas restated in oracle/saltelli.py, unpinned like the rest of
-        the OpenTURNS half).  ``jackknife``: delete-a-group jackknife over the partial-sum slots (disjoint groups of
-        base rows, every rank's slots together), always computed as a cross-check (costs 0.5 ms at N = 1e6) and the
-        fallback when the outputs were not kept."""
+        the exact centring ``c_d`` (``bk_sobol_asymptotic``; formulas restated in oracle/saltelli.py, unpinned like the
+        rest of the OpenTURNS half).  ``jackknife``: delete-a-group jackknife over the partial-sum slots (disjoint
+        groups of base rows, every rank's slots together), always computed as a cross-check (costs 0.5 ms at
+        N = 1e6) and the fallback when the outputs were not kept.  ``abuf`` = [asymptotic sums | number of ranks that
+        kept their outputs]: ONE all-reduce beside the all-gather of the jackknife groups."""
         import torch
         import torch.distributed as dist
-        d = self.details
         dev = partials.device
         jk = torch.empty((nslots, 2 + 2 * p), dtype=torch.float64, device=dev)
         _lib.check(lib.bk_sobol_jackknife(ctypes.c_void_p(partials.data_ptr()), ctypes.c_void_p(totals.data_ptr()),
                                           size, p, F, second, ctypes.c_void_p(jk.data_ptr()), stream))
-        # asymptotic sums on this rank's kept outputs
-        asym = None
+        na = (2 + 6 * p) * 2
+        abuf = torch.zeros(na + 1, dtype=torch.float64, device=dev)
         if kept:
-            center, R = self._interval_geometry(d, keep_basis, kept[0][0].shape[2])
-            asym = torch.zeros((2 + 6 * p, 2), dtype=torch.float64, device=dev)
-            c_d = torch.from_numpy(np.ascontiguousarray(center)).to(dev)
+            # asymptotic sums on this rank's kept outputs, accumulated in place at the head of abuf
             R_d = torch.from_numpy(np.ascontiguousarray(R)).to(dev) if R is not None else None
             zero_d = torch.zeros(R.shape[0] if R is not None else 1, dtype=torch.float64, device=dev)
             for z, cnt in kept:
@@ -474,20 +497,19 @@ class UQ:
                     z = pod_inverse(zero_d, R_d, z.reshape(nbk * cnt, r)).view(nbk, cnt, R.shape[0])
                     r = R.shape[0]
                 _lib.check(lib.bk_sobol_asymptotic(ctypes.c_void_p(z.data_ptr()), cnt, cnt, p, r,
-                                                   ctypes.c_void_p(c_d.data_ptr()), ctypes.c_void_p(asym.data_ptr()), stream))
-        # one buffer for the interval sums: [asymptotic sums | number of ranks that kept their outputs], summed over the
-        # ranks in ONE all-reduce beside the all-gather of the jackknife groups; ONE device -> host copy for both
-        na = (2 + 6 * p) * 2
-        abuf = torch.zeros(na + 1, dtype=torch.float64, device=dev)
-        if asym is not None:
-            abuf[:na] = asym.reshape(-1)
+                                                   ctypes.c_void_p(c_d.data_ptr()), ctypes.c_void_p(abuf.data_ptr()), stream))
             abuf[na] = 1.0
         if world > 1:
             parts = [torch.empty_like(jk) for _ in range(world)]
             dist.all_gather(parts, jk)
             jk = torch.cat(parts, dim=0)
             dist.all_reduce(abuf, op=dist.ReduceOp.SUM)
-        host = torch.cat([abuf, jk.reshape(-1)]).cpu().numpy()
+        return abuf, jk
+
+    def _interval_finish(self, host, size, p, world):
+        """Host half: interval widths from the summed interval sums (``host`` = abuf followed by the jackknife rows)."""
+        d = self.details
+        na = (2 + 6 * p) * 2
         asym = host[:na].reshape(2 + 6 * p, 2) if host[na] == float(world) else None   # every rank kept its outputs, or none is used
         jk = host[na + 1:].reshape(-1, 2 + 2 * p)
         jk = jk[jk[:, 0] > 0]

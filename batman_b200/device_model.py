@@ -200,7 +200,9 @@ class DeviceModel:
         and the results of slice c-1 are downloaded on another (the download blocks the host thread only, the
         GPU already has the next slice's kernels queued).  Pageable arrays are handed to the driver as they are: its
         staged copies (10-20 GB/s) were steadier than a pinned staging ring filled by helper threads, alone and with
-        4 ranks on one host (profiles/r02_e2e_probe*.jsonl)."""
+        4 ranks on one host (profiles/r02_e2e_probe*.jsonl).  Also measured and not kept: downloads on a helper
+        thread (0.325 s per 1.8e7 rows against 0.285 s inline) and result arrays on madvise(MADV_HUGEPAGE) mappings
+        (0.43 s: huge-page faults compact memory on these hosts)."""
         points = np.ascontiguousarray(points, dtype=np.float64)
         k = points.shape[0]
         src = torch.from_numpy(points)

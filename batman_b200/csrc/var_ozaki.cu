@@ -389,7 +389,6 @@ int oz_gang_size(int n_pad, int sms) {
         if (g <= sms && (double)(sms / g) * tile_bytes <= budget) return g;
     return sms >= 37 ? 37 : 2;
 }
-constexpr int OZ_GANG_MAX = 37;
 
 int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, double kappa, long k, double* std_out,
                      double* scratch, int* fail_flag, cudaStream_t st) {

@@ -391,3 +391,24 @@ def test_int8_slicing_of_w_rows_with_wide_dynamic_range(scheme):
           "(of the prior variance)" % (rows.max(), np.log2(max(span)), scheme, err_i, err_f))
     assert err_i <= max(4.0 * err_f, 1e-12)
     torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize('n,p,gang', [(2000, 6, 4), (8100, 6, 16)])
+def test_int8_sigma_gang_sizes_between_the_configs(n, p, gang):
+    """The sigma kernel shares a tile of test points between G CTAs, G chosen from n_train (2 at n = 1024, 8 at 4096,
+    37 at 16384: covered by the config tests).  The sizes in between (G = 4, 16), several tiles per gang and a
+    ragged last tile: int8 kernel against the FP64 DMMA kernel."""
+    st = synthetic_state(n, p, 'matern32', ls=np.full(p, 1.2))
+    k = kriging_from_states([st])
+    rng = np.random.RandomState(11)
+    pts = np.vstack([rng.rand(9001, p), st['X_train'][:7]])
+    model = k._model()
+    model.set_sigma_kernel('dmma')
+    m0, s0 = k.evaluate(pts)
+    model.set_sigma_kernel('int8')
+    m1, s1 = k.evaluate(pts)
+    prior = ogp.kernel_diag(st['tree']) * st['y_std'] ** 2
+    np.testing.assert_array_equal(m0, m1)
+    err = np.max(np.abs(s1 ** 2 - s0 ** 2)) / prior
+    print("n=%d (gang of %d): int8-vs-DMMA %.2e of the prior variance" % (n, gang, err))
+    assert err <= 1e-11

@@ -18,6 +18,9 @@ BUILD = os.path.join(HERE, 'build')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
          '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr']
+# the Saltelli kernels are 50-60 template instantiations per file (10 and 5 minutes of ptxas on one core): their
+# device code is compiled on four threads; every other file keeps the single-threaded code generation it was tuned with
+SPLIT_COMPILE = {'sobol.cu': ['-split-compile', '4'], 'sobol_static.cu': ['-split-compile', '4']}
 
 
 def sources():
@@ -50,7 +53,7 @@ def compile_one(src, force=False):
     newest = max(os.path.getmtime(d) for d in [path, os.path.abspath(__file__)] + sorted(header_deps(path)))
     if not force and os.path.exists(obj) and os.path.getmtime(obj) >= newest:
         return obj
-    r = subprocess.run([NVCC] + FLAGS + ['-c', os.path.join(HERE, src), '-o', obj],
+    r = subprocess.run([NVCC] + FLAGS + SPLIT_COMPILE.get(src, []) + ['-c', os.path.join(HERE, src), '-o', obj],
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     with open(log, 'w') as f:
         f.write(r.stdout)

@@ -35,6 +35,7 @@ SIGNATURES = {
     'bk_gp_set_output_int8': (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
     'bk_gp_set_var_mode': (ctypes.c_int, [vp, ctypes.c_int]),
     'bk_gp_set_overlap': (ctypes.c_int, [vp, ctypes.c_int]),
+    'bk_sigma_gang_size': (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     'bk_gp_set_scaler': (ctypes.c_int, [vp, c_double_p, c_double_p]),
     'bk_pack_w': (ctypes.c_int, [vp, ctypes.c_int, vp, vp]),
     'bk_gp_predict_workspace': (ctypes.c_size_t, [vp, ctypes.c_long, ctypes.c_int]),

@@ -45,6 +45,7 @@ int launch_predict(const bk_gp_s* h, int q, const double* pts, long k, double* m
                    int kq_scheme, double kappa, cudaStream_t st);
 int launch_var_ozaki(const bk_gp_s* h, int q, int scheme, const int8_t* kq, double kappa, long k, double* std_out,
                      double* scratch, int* fail_flag, cudaStream_t st);
+int oz_gang_size(int n_pad, int sms);
 int launch_var(const bk_gp_s* h, int q, const double* kstar, long k, double* std_out, cudaStream_t st);
 int launch_pack_w(const double* w, int n, double* out, cudaStream_t st);
 int launch_sobol(const bk_gp_s* h, int q, const double* a, const double* b, uint64_t seed, const int* mkind,
@@ -316,6 +317,11 @@ int bk_gp_set_output_int8(bk_gp_t h, int q, const int8_t* wq_dev, const double* 
     h->out[q].wq = wq_dev;
     h->out[q].wsig = wsig_dev;
     return 0;
+}
+
+int bk_sigma_gang_size(int n_train, int sm_count) {
+    if (n_train < 1 || sm_count < 1) return 0;
+    return oz_gang_size(padded_n(n_train), sm_count);
 }
 
 int bk_gp_set_overlap(bk_gp_t h, int on) {

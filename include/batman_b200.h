@@ -106,6 +106,9 @@ int bk_gp_set_output_general(bk_gp_t h, int q, int nf, const int* fkind_host, co
 size_t bk_gp_wq_bytes(int n_train);
 int bk_gp_set_output_int8(bk_gp_t h, int q, const int8_t* wq_dev, const double* wsig_dev);
 int bk_gp_set_var_mode(bk_gp_t h, int mode);
+/* CTAs that share one tile of 128 test points in the int8 sigma kernel (csrc/var_ozaki.cu): chosen from n_train so that
+ * the K* tiles in flight (sm_count / G of them, 896 * n_pad bytes each) stay in the L2.  Pure host arithmetic. */
+int bk_sigma_gang_size(int n_train, int sm_count);
 /* on = 1: a sigma prediction of several units (chunks of points x outputs) runs on two internal streams, K1 of unit
  * u+1 (FP64 pipe) beside the sigma kernel of unit u (tensor pipe), on two K* buffers inside the workspace; the
  * caller's stream forks into them and joins again before bk_gp_predict returns.  on = 0 (default): every kernel on the

@@ -302,3 +302,17 @@ def test_lockstep_batcher_propagates_failures_without_deadlock():
     [t.start() for t in threads]
     [t.join(timeout=20) for t in threads]
     assert len(errs) == 2 and all(isinstance(e.__cause__, ValueError) for e in errs)
+
+
+def test_sigma_kernel_gang_size_policy():
+    """CTAs per tile of test points in the int8 sigma kernel: the K* tiles in flight (SMs / G tiles of 896 n_pad bytes)
+    must fit in about half of the 126 MB L2 of a B200 (148 SMs), and G never exceeds the SM count."""
+    from batman_b200 import _lib
+    lib = _lib.load()
+    want = {100: 2, 1024: 2, 2000: 4, 4096: 8, 8192: 16, 16384: 37}
+    for n, g in want.items():
+        assert lib.bk_sigma_gang_size(n, 148) == g, n
+        n_pad = lib.bk_gp_padded_n(n)
+        assert (148 // g) * n_pad * 896 <= 72e6
+    assert lib.bk_sigma_gang_size(16384, 16) <= 16
+    assert lib.bk_sigma_gang_size(0, 148) == 0

@@ -10,7 +10,8 @@ reference's ``gp.predict(return_std=True)`` computes per row,
 kriging.py:210-212).  ``value`` = rows / s with the design resident in HBM;
 ``e2e`` = the same through ``SurrogateModel.__call__`` with a plain (pageable)
 numpy array in and numpy arrays out, host<->device copies in the timed region
-(``e2e_pinned``: the same from a pinned buffer).  ``sobol`` = ``UQ.sobol()``
+(median of five calls after one untimed call, every call in ``e2e.runs_s``;
+``e2e_pinned``: the same from a pinned buffer).  ``sobol`` = ``UQ.sobol()``
 itself (fused mean-only path: the reference discards sigma in uq.py:201-202),
 timed inside the clock-sampled region, all-reduce included.
 
@@ -22,7 +23,8 @@ is the strong-scaling point (the SAME N = 1e6 experiment split over G GPUs),
 unsharded run of the same experiment on rank 0.
 
 ``roofline`` is quoted on the pipe the dominant kernel runs on: int8 tensor
-ops of k_var_ozaki over the measured ``tcgen05.mma kind::i8`` peak; the
+ops of k_var_ozaki over the measured SUSTAINED ``tcgen05.mma kind::i8`` rate
+(the kernel is timed inside a long step; the burst rate is reported too); the
 FP64-equivalent rate is reported beside it.  ``roofline_sobol`` does the same
 for the fused Saltelli kernel (FP64 pipe).  ``north_star`` and ``configs``
 carry the other BASELINE configurations at their model sizes.
